@@ -1,0 +1,171 @@
+"""TEST INFRASTRUCTURE ONLY -- loader for the UNMODIFIED reference KS environment.
+
+Only ``tests/``, ``tests/golden/make_golden.py`` and ``oracle/`` self-checks may import this.
+Nothing on the product path (``model_based_pde_control_b200``) may import anything under
+``oracle/``.
+
+The reference (``/root/reference``, read-only, present in the build container only) cannot be
+imported as-is:
+
+* ``pdegym/__init__.py:2`` imports a ``pdegym.burgers`` package that is not in the tree
+  -> a bare ``pdegym`` package object with the right ``__path__`` is registered instead;
+* ``pdegym/kuramoto/kuramoto.py:4`` imports ``gym`` (0.25.2, not installed, no network)
+  -> a stub exposing exactly the attributes the reference touches;
+* ``pdegym/common/transforms.py:7`` imports ``pdecontrol.mbrl.types`` which imports
+  ``pytorch_lightning`` (``pdecontrol/mbrl/types.py:6``) -> stub module.
+
+With those three stubs ``KuramotoSivashinskyEnv`` constructs and ``step``/``reset``/``rhs``/
+``forcing`` execute the reference's own code, byte for byte.  This file contains no reference
+code; it only arranges ``sys.modules`` so that the reference's files can be executed where they
+lie.
+"""
+from __future__ import annotations
+
+import os
+import sys
+import types
+
+import numpy as np
+
+REFERENCE_ROOTS = (
+    os.environ.get("KS_REFERENCE_ROOT", ""),
+    "/root/reference",
+)
+
+
+def reference_root() -> str | None:
+    for root in REFERENCE_ROOTS:
+        if root and os.path.isfile(os.path.join(root, "pdegym", "kuramoto", "kuramoto.py")):
+            return root
+    return None
+
+
+def reference_available() -> bool:
+    return reference_root() is not None
+
+
+class _Box:
+    """Just enough of ``gym.spaces.Box`` for ``kuramoto.py:75-76``."""
+
+    def __init__(self, low, high, shape=None, dtype=np.float32):
+        self.dtype = np.dtype(dtype)
+        if shape is None:
+            shape = np.shape(low)
+        self.shape = tuple(shape)
+        self.low = np.broadcast_to(np.asarray(low, dtype=self.dtype), self.shape).copy()
+        self.high = np.broadcast_to(np.asarray(high, dtype=self.dtype), self.shape).copy()
+
+    def sample(self):
+        lo = np.where(np.isfinite(self.low), self.low, -1.0)
+        hi = np.where(np.isfinite(self.high), self.high, 1.0)
+        return np.random.uniform(lo, hi, size=self.shape).astype(self.dtype)
+
+
+class _Env:
+    """Just enough of ``gym.Env``."""
+
+    metadata: dict = {}
+
+    @property
+    def unwrapped(self):
+        return self
+
+
+class _Wrapper:
+    def __init__(self, env, *args, **kwargs):
+        self.env = env
+
+    def __getattr__(self, name):
+        return getattr(self.env, name)
+
+    @property
+    def unwrapped(self):
+        return self.env.unwrapped
+
+
+def _install_stubs(root: str) -> None:
+    if "gym" not in sys.modules:
+        gym = types.ModuleType("gym")
+        gym.Env = _Env
+        gym.Wrapper = _Wrapper
+        spaces = types.ModuleType("gym.spaces")
+        spaces.Box = _Box
+        gym.spaces = spaces
+        envs = types.ModuleType("gym.envs")
+        envs.register = lambda *a, **k: None
+        gym.envs = envs
+        wrappers = types.ModuleType("gym.wrappers")
+        wrappers.TimeLimit = _Wrapper
+        wrappers.RescaleAction = _Wrapper
+        gym.wrappers = wrappers
+        core = types.ModuleType("gym.core")
+        core.ObservationWrapper = _Wrapper
+        core.ActionWrapper = _Wrapper
+        gym.core = core
+        gym.ObservationWrapper = _Wrapper
+        gym.ActionWrapper = _Wrapper
+        vector = types.ModuleType("gym.vector")
+        vector.VectorEnv = type("VectorEnv", (), {})
+        vector.VectorEnvWrapper = type("VectorEnvWrapper", (), {})
+        gym.vector = vector
+        sys.modules.update({
+            "gym": gym, "gym.spaces": spaces, "gym.envs": envs, "gym.wrappers": wrappers,
+            "gym.core": core, "gym.vector": vector,
+        })
+    if "pytorch_lightning" not in sys.modules:
+        pl = types.ModuleType("pytorch_lightning")
+        pl.Trainer = type("Trainer", (), {})
+        pl.Callback = type("Callback", (), {})
+        pl.LightningModule = type("LightningModule", (), {})
+        pl.LightningDataModule = type("LightningDataModule", (), {})
+        sys.modules["pytorch_lightning"] = pl
+    # bare package objects: the reference's own ``__init__`` files are NOT executed
+    for pkg in ("pdegym", "pdegym.common", "pdegym.kuramoto", "pdecontrol", "pdecontrol.mbrl"):
+        if pkg not in sys.modules:
+            mod = types.ModuleType(pkg)
+            mod.__path__ = [os.path.join(root, *pkg.split("."))]
+            sys.modules[pkg] = mod
+
+
+_CACHE: dict = {}
+
+
+def load_reference():
+    """Return ``(kuramoto_module, transforms_module)`` executed from the reference tree."""
+    if "mods" in _CACHE:
+        return _CACHE["mods"]
+    root = reference_root()
+    if root is None:
+        raise RuntimeError("reference tree not available (expected /root/reference)")
+    _install_stubs(root)
+    import importlib.util
+
+    def _load(name, relpath):
+        if name in sys.modules:
+            return sys.modules[name]
+        spec = importlib.util.spec_from_file_location(name, os.path.join(root, relpath))
+        mod = importlib.util.module_from_spec(spec)
+        sys.modules[name] = mod
+        spec.loader.exec_module(mod)
+        return mod
+
+    _load("pdecontrol.mbrl.types", "pdecontrol/mbrl/types.py")
+    transforms = _load("pdegym.common.transforms", "pdegym/common/transforms.py")
+    kuramoto = _load("pdegym.kuramoto.kuramoto", "pdegym/kuramoto/kuramoto.py")
+    _CACHE["mods"] = (kuramoto, transforms)
+    return _CACHE["mods"]
+
+
+def make_reference_env(Xi=None, **config):
+    """Construct the reference's ``KuramotoSivashinskyEnv`` (optionally with other jets).
+
+    ``Xi`` is a class attribute in the reference (``kuramoto.py:18``); other jet layouts are
+    obtained the only way the reference allows: by subclassing.  ``noop`` is hard-coded to 4
+    jets (``kuramoto.py:62``) and ``reset`` steps with a 4-vector (``kuramoto.py:109``), so a
+    J != 4 subclass can ``step`` but not ``reset``.
+    """
+    kuramoto, _ = load_reference()
+    cls = kuramoto.KuramotoSivashinskyEnv
+    if Xi is not None:
+        cls = type("KuramotoSivashinskyEnvXi", (cls,), {"Xi": list(Xi)})
+    return cls(**config)
