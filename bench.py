@@ -1,0 +1,370 @@
+#!/usr/bin/env python
+"""bench.py -- KS env control-periods/s on N B200s (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]              # this repo's CUDA path
+    python bench.py --impl reference [--gpus N] [--steps K] ...      # the reference's CPU path
+
+A "step" is one control period (250 RK4 sub-steps) of every env of the workload:
+``configs[1]`` of BASELINE.json at N=1 -- 4096 batched KS envs, default grid (N=64, L=22, 4 jets),
+fp64, random actions -- and the same 4096 envs PER GPU at N>1 (weak scaling; each rank owns a
+contiguous env shard, and the per-period NCCL all-gather of obs/reward/flags is inside the timed
+region).  One JSON line on stdout (rank 0).  See DESIGN.md "Measurement" for every field.
+
+Timed regions
+* ``value``: K x ``ks_step`` with actions already resident in HBM, CUDA events around every
+  step on the launching stream, L2 flushed between timed steps, max over ranks.
+* ``e2e``: K x ``KSVecEnv.step(numpy actions)`` -- the call a user of the gym API makes -- host
+  buffers, H2D + kernel + D2H + sync inside the region (wall clock around synchronous calls).
+* ``cpu_baseline`` / ``--impl reference``: the oracle's NumPy/SciPy port of the reference's
+  ``step`` (same third-party calls the reference makes) on every host core.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import multiprocessing as mp
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "ks_control_periods_per_s"
+UNIT = "control-periods/s"
+ENVS_PER_GPU = 4096
+FLOPS_PER_POINT_SUBSTEP = 191          # un-merged stencils, mul/add = 1 flop, FMA = 2
+FP64_NOMINAL_TFLOPS = 37.2             # 148 SM x 64 lanes x 2 x 1.965 GHz
+
+
+# -------------------------------------------------------------------------------------------------
+# CPU reference arm / cpu_baseline (oracle port; the ONLY place bench.py touches oracle/)
+# -------------------------------------------------------------------------------------------------
+def _cpu_worker(args):
+    """One process = one env stepped with the reference-style NumPy/SciPy port, single-threaded."""
+    seed, periods, warm = args
+    os.environ.setdefault("OMP_NUM_THREADS", "1")
+    import numpy as np
+    try:
+        import torch
+        torch.set_num_threads(1)
+    except Exception:
+        pass
+    from oracle import ks_numpy as ko
+
+    cfg = ko.KSConfig()
+    F = ko.forcing_matrix(cfg)
+    rng = np.random.default_rng(seed)
+    u = rng.uniform(-0.4, 0.4, (1, cfg.N))
+    acts = rng.uniform(-1, 1, (warm + periods, 1, cfg.J)).astype(np.float32)
+    for k in range(warm):
+        u, _ = ko.step(cfg, u, ko.forcing(acts[k], F), rhs_fn=ko.rhs_scipy)
+    t0 = time.perf_counter()
+    for k in range(warm, warm + periods):
+        u, _ = ko.step(cfg, u, ko.forcing(acts[k], F), rhs_fn=ko.rhs_scipy)
+    return time.perf_counter() - t0, float(np.abs(u).max())
+
+
+def cpu_port_throughput(periods_per_proc: int, procs: int | None = None, warm: int = 1):
+    """Aggregate control-periods/s of ``procs`` independent single-env processes (the reference's
+    own parallelism is one process per env, mbrl.py:81-86)."""
+    procs = procs or os.cpu_count() or 1
+    ctx = mp.get_context("spawn")
+    t0 = time.perf_counter()
+    with ctx.Pool(procs) as pool:
+        res = pool.map(_cpu_worker, [(1000 + i, periods_per_proc, warm) for i in range(procs)])
+    wall = time.perf_counter() - t0
+    slowest = max(r[0] for r in res)
+    return procs * periods_per_proc / slowest, procs, wall
+
+
+def cpu_c_port_throughput(envs: int = 64, periods: int = 4):
+    """The plain-C oracle on all cores (context: how fast a compiled CPU port is)."""
+    import numpy as np
+    from oracle import ks_c, ks_numpy as ko
+
+    cfg = ko.KSConfig()
+    rng = np.random.default_rng(0)
+    u = rng.uniform(-0.4, 0.4, (envs, cfg.N))
+    phi = np.zeros((envs, cfg.N), np.float32)
+    u, _ = ks_c.step(cfg, u, phi)
+    t0 = time.perf_counter()
+    for _ in range(periods):
+        u, _ = ks_c.step(cfg, u, phi)
+    dt = time.perf_counter() - t0
+    return envs * periods / dt, ks_c.num_threads()
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    steps, warm = max(1, args.steps), max(0, args.warmup)
+    procs = os.cpu_count() or 1
+    # bounded sample: each "step" = one control period of one env per host core
+    per_proc = min(steps, 40)
+    thr, procs, wall = cpu_port_throughput(per_proc, procs, warm=min(warm, 2))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": thr, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": per_proc, "warmup": min(warm, 2), "ms_per_step": 1e3 * procs / thr,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "KuramotoSivashinskyEnv-v0 step, default grid N=64 L=22 J=4, cfg_steps=250, "
+                               "random actions; one env per host core (the reference's process-per-env parallelism)"},
+        "cpu_baseline": {"value": thr, "unit": UNIT, "cores": procs, "kind": "port",
+                         "sample": f"{procs} processes x {per_proc} control periods of 1 env each, NumPy/SciPy port "
+                                   "of the reference step (scipy.ndimage.convolve1d stencils, per-sub-step reward)"},
+        "e2e": {"value": thr, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# -------------------------------------------------------------------------------------------------
+# GPU arm
+# -------------------------------------------------------------------------------------------------
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu_index = gpu_index
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.gpu_index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ""
+        sm, smmax, power, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in out.strip().splitlines():
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smmax.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        # "under load" = samples in the upper half of the observed power range
+        thr = (max(power) + min(power)) / 2 if len(power) > 1 else 0.0
+        loaded = [c for c, p in zip(sm, power) if p >= thr] or sm
+        return {"sm_mhz": statistics.median(loaded), "sm_max_mhz": max(smmax), "power_w_max": max(power),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def run_gpu_arm(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from model_based_pde_control_b200 import KSVecEnv, _lib
+    from model_based_pde_control_b200.sharding import gather_batch
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.gpus != world and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    B = args.envs_per_gpu
+    K, W = args.steps, max(3, args.warmup)
+    env = KSVecEnv(B, device=local_rank, precision=args.precision, points_per_lane=args.points_per_lane)
+    N, J, S = env.N, env.J, env.cfg_steps
+    total_envs = B * world
+
+    # synthetic workload: seeded ICs, short device burn-in onto the attractor,
+    # random actions for every timed period, all resident in HBM before timing starts
+    rng = np.random.default_rng(1000 + rank)
+    env.set_state(rng.uniform(-0.4, 0.4, (B, N)), 0)
+    env.rollout_device(None, K=args.burnin, outputs=False)
+    env.set_state(None, 0)
+    actions = torch.as_tensor(rng.uniform(-1, 1, (W + K, B, J)).astype(np.float32)).to(dev)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
+    stream = torch.cuda.current_stream(dev)
+
+    def one_step(k):
+        out = env.step_device(actions[k])
+        if world > 1:
+            out = gather_batch({"obs": out["obs"], "reward": out["reward"], "truncated": out["truncated"]}, total_envs)
+        return out
+
+    for k in range(W):
+        one_step(k)
+    torch.cuda.synchronize(dev)
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    stops = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    launches0 = env.launch_count
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    wall0 = time.perf_counter()
+    for k in range(K):
+        flush.zero_()                      # L2 flush between timed steps (outside the event pair)
+        starts[k].record(stream)
+        one_step(W + k)
+        stops[k].record(stream)
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    wall = time.perf_counter() - wall0
+    launches = env.launch_count - launches0
+    step_ms = [s.elapsed_time(e) for s, e in zip(starts, stops)]
+    total_ms = sum(step_ms)
+    if world > 1:
+        t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    clocks = sampler.stop() if rank == 0 else None
+    flags_bad = bool(env.nonfinite().any())
+
+    # ---- e2e: the gym-facing host API, host buffers, copies inside the timed region ----
+    acts_host = rng.uniform(-1, 1, (W + K, B, 1, J)).astype(np.float32)
+    env.set_state(None, 0)
+    for k in range(W):
+        env.step(acts_host[k])
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    for k in range(K):
+        obs, rew, term, trunc, info = env.step(acts_host[W + k])
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_value = total_envs * K / e2e_s
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return 0
+
+    # ---- roofline of the dominant (only) kernel ----
+    kernel_ms = total_ms / K            # N=1: the event pair brackets exactly one kernel launch
+    value = total_envs * K / (total_ms * 1e-3)
+    flops_per_launch = FLOPS_PER_POINT_SUBSTEP * N * S * B
+    achieved_tf = flops_per_launch / (kernel_ms * 1e-3) / 1e12
+    lib = _lib.load()
+    best, mean = ctypes.c_double(), ctypes.c_double()
+    rc = lib.ks_bench_fp64_peak(local_rank, 20000, 5, ctypes.byref(best), ctypes.byref(mean))
+    fp64_peak = best.value if rc == 0 and best.value > 0 else FP64_NOMINAL_TFLOPS
+    peak_src = "self-measured DFMA micro-kernel (ks_bench_fp64_peak, best of 5)" if rc == 0 else "nominal"
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    hbm_src = "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    esz = 8 if args.precision == "f64" else 4
+    bytes_per_launch = (2 * esz * N + 4 * N + 4 * J + 16) * B     # 20N+4J+16 per env (fp64)
+    hbm_achieved = bytes_per_launch / (kernel_ms * 1e-3) / 1e9
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": args.precision, "data": "synthetic",
+        "config": {
+            "workload": f"{B} KS envs per GPU x {world} GPU(s) = {total_envs} envs, N={N} L={env.L} J={J}, "
+                        f"cfg_steps={S} RK4 sub-steps per control period, dt={env.dt}, {args.precision}, "
+                        "random actions (BASELINE.json configs[1] per GPU)",
+            "envs_per_gpu": B, "total_envs": total_envs, "N": N, "J": J, "cfg_steps": S,
+            "l2": "flushed (256 MiB memset) between timed steps, outside the per-step event pairs",
+            "collective": "none (N=1)" if world == 1 else "NCCL all-gather of obs/reward/truncated per period, timed",
+            "layout": env.launch_info(),
+        },
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": env.h2d_bytes_per_step,
+                "d2h_bytes_per_step": env.d2h_bytes_per_step, "ms_per_step": 1e3 * e2e_s / K,
+                "api": "KSVecEnv.step(numpy actions) -> ks_step_host (pinned H2D, kernel, packed D2H, sync)"},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": {
+            "bound": "fp64", "kernel": "ks_period_kernel", "achieved": achieved_tf, "peak": fp64_peak,
+            "unit": "TFLOP/s", "frac": achieved_tf / fp64_peak, "traffic": None,
+            "peak_source": peak_src, "peak_nominal": FP64_NOMINAL_TFLOPS, "frac_of_nominal": achieved_tf / FP64_NOMINAL_TFLOPS,
+            "flops_per_launch": flops_per_launch, "flops_model": "191*N*cfg_steps per env-period (SURVEY.md 8d)",
+            "kernel_ms": kernel_ms,
+            "hbm": {"achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_achieved / hbm_peak,
+                    "bytes_per_launch": bytes_per_launch, "peak_source": hbm_src},
+        },
+        "wall_s_timed_region": wall,
+        "nonfinite": flags_bad,
+    }
+
+    # ---- CPU baseline on this box's host cores (rank 0, N=1 only; bounded sample) ----
+    if world == 1 and not args.no_cpu_baseline:
+        thr, procs, cpu_wall = cpu_port_throughput(args.cpu_periods)
+        line["cpu_baseline"] = {
+            "value": thr, "unit": UNIT, "cores": procs, "kind": "port",
+            "sample": f"{procs} processes x {args.cpu_periods} control periods of 1 env each (default grid), NumPy/SciPy "
+                      f"port of the reference step; {cpu_wall:.1f} s wall"}
+        try:
+            cthr, cthreads = cpu_c_port_throughput()
+            line["cpu_baseline_c"] = {"value": cthr, "unit": UNIT, "cores": cthreads, "kind": "port",
+                                      "sample": "plain-C oracle (oracle/ks_oracle.c, -O2, pthreads), 64 envs x 4 periods"}
+        except Exception as exc:   # the C oracle is optional context
+            line["cpu_baseline_c"] = {"error": str(exc)}
+    print(json.dumps(line), flush=True)
+    env.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--envs-per-gpu", type=int, default=ENVS_PER_GPU)
+    ap.add_argument("--precision", default="f64", choices=["f64", "f32"])
+    ap.add_argument("--points-per-lane", type=int, default=0)
+    ap.add_argument("--burnin", type=int, default=40, help="device burn-in periods before timing")
+    ap.add_argument("--cpu-periods", type=int, default=20, help="control periods per host core for cpu_baseline")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+    return run_gpu_arm(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,156 @@
+/* ks_b200.h -- C ABI of libks_b200.so: batched Kuramoto-Sivashinsky control environment,
+ * hand-written CUDA for NVIDIA B200 (sm_100a).
+ *
+ * The reference (stwerner97/model-based-pde-control) is pure Python and has no FFI; the
+ * interface this library replaces is the gym 0.25.2 Env / VectorEnv protocol as exercised by
+ *   pdegym/kuramoto/kuramoto.py:78-116          KuramotoSivashinskyEnv.step / reset
+ *   pdegym/common/transforms.py:250-265         GaussianForcing (jet actuation, float32)
+ *   pdegym/kuramoto/__init__.py:8-12            make(): TimeLimit(env, 400)
+ *   pdecontrol/mbrl/mbrl.py:81-86               gym.vector.make(env_id, num_envs=cpus)
+ *   pdecontrol/mbrl/worker.py:48-66             envs.reset() / envs.step(actions)
+ * Each entry point below cites the reference lines it stands in for.  The Python mirror of the
+ * gym surface (KSVecEnv) binds these with ctypes; INTEGRATION.md shows the stub.
+ *
+ * Conventions
+ *   - every function returns int: 0 = OK, < 0 = argument / state error (the device is not
+ *     touched), > 0 = a cudaError_t value.  ks_last_error() gives a message for the last
+ *     non-zero return on that handle (or on creation, with a NULL handle).
+ *   - no C++ exceptions, callbacks or global mutable state cross the boundary; no allocations
+ *     after ks_create.
+ *   - the caller owns every buffer it passes.  "dev" pointers are device memory on the
+ *     handle's device; "host" pointers are ordinary (ideally pinned) host memory.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = the legacy default stream).  Device
+ *     entry points are asynchronous and stream-ordered; *_host entry points synchronise the
+ *     stream before returning.
+ *   - a handle is bound to one device and is not thread-safe.  Multi-GPU = one process and one
+ *     handle per GPU; envs are independent, so no collective is needed inside the library.
+ *   - there is no CPU fallback: without a usable CUDA device ks_create fails.
+ */
+#ifndef KS_B200_H
+#define KS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KS_ABI_VERSION 1
+
+enum ks_precision { KS_F64 = 0, KS_F32 = 1 };
+/* KS_REWARD_L2: what the reference executes, -(1/N)*||u||^2 (kuramoto.py:64-65,72).
+ * KS_REWARD_DISSIPATION: the intended -(mean(uxx^2)+mean(ux^2)+mean(u*phi)) (kuramoto.py:67-70). */
+enum ks_reward_mode { KS_REWARD_L2 = 0, KS_REWARD_DISSIPATION = 1 };
+enum ks_where { KS_HOST = 0, KS_DEVICE = 1 };
+
+enum ks_error {
+    KS_OK = 0,
+    KS_ERR_ARG = -1,         /* NULL / out-of-range argument */
+    KS_ERR_UNSUPPORTED = -2, /* grid size N cannot be mapped to the register kernel */
+    KS_ERR_NO_DEVICE = -3,   /* no CUDA device / wrong architecture */
+    KS_ERR_STATE = -4        /* call not valid in the handle's current state */
+};
+
+/* Constants of KuramotoSivashinskyEnv.__init__ (kuramoto.py:29-57) plus batch geometry. */
+typedef struct ks_config {
+    int32_t abi_version;       /* = KS_ABI_VERSION */
+    int32_t num_envs;          /* B: independent environments owned by this handle */
+    int32_t N;                 /* grid points (reference default 64) */
+    int32_t J;                 /* jets = len(Xi) (reference default 4), 0 < J <= 32 */
+    int32_t cfg_steps;         /* RK4 sub-steps per control period (250) */
+    int32_t max_episode_steps; /* ceil(Tmax/(dt*cfg_steps)) = 400 (kuramoto.py:57) */
+    int32_t burnin_periods;    /* int(200/dt/cfg_steps) = 800 (kuramoto.py:103) */
+    int32_t precision;         /* enum ks_precision */
+    int32_t reward_mode;       /* enum ks_reward_mode */
+    int32_t device;            /* CUDA device ordinal */
+    int32_t points_per_lane;   /* 0 = choose automatically; else P with N % P == 0, 4<=P<=16 */
+    int32_t reserved;
+    double L;                  /* domain length (22.0) */
+    double dt;                 /* RK4 step (1e-3) */
+    const float *forcing;      /* host, [J*N] row-major float32: GaussianForcing.forcing
+                                  (transforms.py:258-260), built by the caller with torch so that
+                                  it is bit-identical to the reference's matrix */
+} ks_config;
+
+typedef struct ks_handle ks_handle;
+
+/* Replaces KuramotoSivashinskyEnv(**config) x num_envs (kuramoto.py:29-76; mbrl.py:81-86).
+ * Allocates u [B,N], timestep [B], flags [B] and the packed output block on `device`; state
+ * starts at u = 0, timestep = 0. */
+int ks_create(const ks_config *cfg, ks_handle **out);
+int ks_destroy(ks_handle *h); /* idempotent on NULL */
+
+/* env.u = ...; env.timestep = ... (plain attributes in the reference; kuramoto.py:105-106).
+ * u is [B,N] float64 whatever the precision (converted on device in KS_F32 mode); either
+ * pointer may be NULL to leave that part unchanged.  Clears the non-finite flags. */
+int ks_set_state(ks_handle *h, const double *u, const int32_t *timestep, int where, void *stream);
+int ks_get_state(ks_handle *h, double *u, int32_t *timestep, int where, void *stream);
+
+/* KuramotoSivashinskyEnv.reset (kuramoto.py:100-116): initial condition, then `burnin_periods`
+ * no-op control periods in ONE launch, then timestep = 0 -- for every env, or only for the envs
+ * with mask[b] != 0 when `mask` is given (gym's vector env resets sub-envs individually when they
+ * truncate).  `where` says where u0 and mask live (KS_HOST / KS_DEVICE).
+ *   u0 != NULL: [B,N] float64 initial condition used verbatim (rows of unmasked envs ignored);
+ *               host NumPy draws give parity with np.random.seed(seed); np.random.uniform(-0.4,0.4,N);
+ *   u0 == NULL: U(-0.4,0.4) from a counter-based Philox generator keyed by (seed; point, env).
+ * burnin_periods < 0 uses the configured value; 0 skips the burn-in. */
+int ks_reset(ks_handle *h, const double *u0, const uint8_t *mask, int where, uint64_t seed,
+             int32_t burnin_periods, void *stream);
+
+/* KuramotoSivashinskyEnv.step for all B envs (kuramoto.py:78-98), one launch, device buffers.
+ *   actions  dev [B,J] float32 (np.array(action, float32), kuramoto.py:79)
+ *   phi      dev [B,N] float32 or NULL; non-NULL overrides the in-kernel `a @ F` FMA chain
+ *   obs      dev [B,N] float32: float32 cast of the new state (what gym's vector env hands on)
+ *   reward   dev [B]   float64: mean over sub-steps of the pre-step reward (kuramoto.py:84,96)
+ *   truncated dev [B]  uint8:   timestep >= max_episode_steps (kuramoto.py:93)
+ *   step     dev [B]   int32:   info["step"] (kuramoto.py:98)
+ *   nonfinite dev [B]  uint8:   1 once the env's state left the finite range (np.seterr(over=
+ *                               "raise"), kuramoto.py:12, raises FloatingPointError at that point)
+ * Any output pointer may be NULL.  No auto-reset here: the caller (KSVecEnv) does it. */
+int ks_step(ks_handle *h, const float *actions, const float *phi, float *obs, double *reward,
+            uint8_t *truncated, int32_t *step, uint8_t *nonfinite, void *stream);
+
+/* K consecutive control periods in one persistent launch (open loop, no auto-reset):
+ * actions dev [K,B,J] (NULL = no-op periods); outputs dev [K,B,...] or NULL. */
+int ks_rollout(ks_handle *h, int32_t K, const float *actions, float *obs, double *reward,
+               uint8_t *truncated, int32_t *step, uint8_t *nonfinite, void *stream);
+
+/* Host-buffer form of ks_step -- the call the gym-facing wrapper makes when the policy lives on
+ * the host (worker.py:60-66): copies actions host->device, runs the period, copies ONE packed
+ * output block device->host and synchronises.  Layout of the block (see ks_out_layout):
+ *   reward f64 [B] | obs f32 [B*N] | step i32 [B] | truncated u8 [B] | nonfinite u8 [B]
+ * (each part 16-byte aligned). */
+int ks_step_host(ks_handle *h, const float *actions_host, void *out_host, void *stream);
+/* offsets[5] = byte offsets of {reward, obs, step, truncated, nonfinite}; *total = block bytes. */
+int ks_out_layout(const ks_handle *h, size_t offsets[5], size_t *total);
+
+/* Mirrors np.seterr(over="raise") (kuramoto.py:12): flags[b] != 0 once env b's state went
+ * non-finite (sticky until ks_reset / ks_set_state).  Synchronises `stream`.  *any (nullable)
+ * receives the OR of all flags; nonfinite_host (nullable) the [B] flags. */
+int ks_status(ks_handle *h, uint8_t *nonfinite_host, int32_t *any, void *stream);
+
+/* Batched evaluation of rhs() and the reward on arbitrary states, for callers that use
+ * env.rhs / env.reward_func offline (training.py:211-236; mbrl/world/world.py:170):
+ * u dev [M,N] f64, phi dev [M,N] f32; outputs (each nullable) dev [M,N] f64 / reward dev [M] f64
+ * with the handle's reward_mode.  Always float64. */
+int ks_eval(ks_handle *h, int32_t M, const double *u, const float *phi, double *rhs, double *ux,
+            double *uxx, double *uxxxx, double *reward, void *stream);
+
+/* Measurement helper (not part of the env path): FP64 FMA throughput of `device` in TFLOP/s from
+ * a register-resident DFMA loop, best and mean over `repeats` launches of `iters` iterations x 16
+ * independent chains per thread.  Used by bench.py as the self-measured FP64 roofline peak. */
+int ks_bench_fp64_peak(int device, int iters, int repeats, double *tflops_best, double *tflops_mean);
+
+/* Introspection */
+int ks_get_config(const ks_handle *h, ks_config *out); /* forcing pointer is returned NULL */
+int ks_launch_info(const ks_handle *h, int32_t *points_per_lane, int32_t *lanes_per_env,
+                   int32_t *block_threads, int32_t *grid_blocks, int32_t *regs_per_thread);
+uint64_t ks_launch_count(const ks_handle *h); /* kernels launched through this handle so far */
+const char *ks_last_error(const ks_handle *h);
+int ks_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KS_B200_H */

@@ -1,0 +1,572 @@
+// ks_api.cu -- C-ABI layer of libks_b200.so (see include/ks_b200.h for the contract and the
+// reference lines each entry point replaces).  Host-side bookkeeping only: every numerical
+// operation runs in the CUDA kernels of ks_kernels.cuh / this file; there is no CPU fallback.
+#include "../../include/ks_b200.h"
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "ks_dispatch.h"
+
+namespace {
+
+// Finite-difference weights, stencil order (kuramoto.py:24-27 after un-flipping convolve1d).
+constexpr double kUpwind[5] = {-25.0 / 12.0, 4.0, -3.0, 4.0 / 3.0, -1.0 / 4.0};
+constexpr double kD2[4] = {-49.0 / 18.0, 3.0 / 2.0, -3.0 / 20.0, 1.0 / 90.0};            // centre, +-1..3
+constexpr double kD4[5] = {91.0 / 8.0, -122.0 / 15.0, 169.0 / 60.0, -2.0 / 5.0, 7.0 / 240.0};  // centre, +-1..4
+
+thread_local char g_create_error[256] = "";
+
+inline size_t align16(size_t x) { return (x + 15) & ~size_t(15); }
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int dev)
+    {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != dev) ok = cudaSetDevice(dev) == cudaSuccess;
+    }
+    ~DeviceGuard()
+    {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+}  // namespace
+
+struct ks_handle {
+    ks_config cfg;
+    int P = 0, lanes = 0, envs_per_warp = 0, grid = 0, regs = 0;
+    const void *kernel = nullptr;
+    ks::Coef<double> c64;
+    ks::Coef<float> c32;
+    // device memory
+    void *u = nullptr;          // [B,N] double or float
+    int32_t *timestep = nullptr;
+    uint8_t *nonfinite = nullptr;
+    float *F = nullptr;         // [J,N]
+    float *actions = nullptr;   // [B,J] staging for ks_step_host
+    uint8_t *out = nullptr;     // packed output block
+    double *scratch64 = nullptr;  // [B,N] f64 staging for set/get_state in F32 mode and host ICs
+    uint8_t *mask = nullptr;      // [B] staging for host reset masks
+    size_t out_off[5] = {0, 0, 0, 0, 0}, out_total = 0;
+    uint64_t launches = 0;
+    char err[256] = "";
+};
+
+namespace {
+
+int fail(ks_handle *h, int code, const char *fmt, ...)
+{
+    char *dst = h ? h->err : g_create_error;
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(dst, 256, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+int cuda_fail(ks_handle *h, cudaError_t e, const char *what)
+{
+    cudaGetLastError();  // clear the sticky-less error state
+    return fail(h, (int)e, "%s: %s (%s)", what, cudaGetErrorName(e), cudaGetErrorString(e));
+}
+
+#define KS_CUDA(h, call)                                      \
+    do {                                                      \
+        cudaError_t e__ = (call);                             \
+        if (e__ != cudaSuccess) return cuda_fail(h, e__, #call); \
+    } while (0)
+
+template <typename T>
+void fill_coef(ks::Coef<T> &c, double dx, double dt)
+{
+    const double dx2 = dx * dx, dx4 = dx2 * dx2;
+    for (int k = 0; k < 5; ++k) {
+        const double d2 = k < 4 ? kD2[k] : 0.0;
+        c.W[k] = (T)(-(kD4[k] / dx4 + d2 / dx2));
+        c.A[k] = (T)(kUpwind[k] * (-0.5) / dx);
+    }
+    for (int k = 0; k < 4; ++k) c.D2[k] = (T)(kD2[k] / dx2);
+    c.dt_half = (T)(dt / 2.0);
+    c.dt_full = (T)dt;
+    c.dt_sixth = (T)(dt / 6.0);
+}
+
+// Points per lane for a grid of N points: lanes = N / P must fit one warp.  Preference: the
+// best lane utilisation (envs_per_warp * lanes / 32), then P = 8 (measured sweet spot between
+// halo overhead and registers), then the larger P.
+int choose_points_per_lane(int N)
+{
+    int best = 0;
+    double best_score = -1.0;
+    for (int P = ks::kMinP; P <= ks::kMaxP; ++P) {
+        if (N % P) continue;
+        const int lanes = N / P;
+        if (lanes < 1 || lanes > 32) continue;
+        const double util = double((32 / lanes) * lanes) / 32.0;
+        const double score = util * 100.0 + (P == 8 ? 2.0 : 0.0) + P * 0.01;
+        if (score > best_score) { best_score = score; best = P; }
+    }
+    return best;
+}
+
+// ---------------------------------------------------------------------------------------------
+// auxiliary kernels
+// ---------------------------------------------------------------------------------------------
+__global__ void convert_f64_to_f32(const double *__restrict__ src, float *__restrict__ dst, size_t n)
+{
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = (float)src[i];
+}
+__global__ void convert_f32_to_f64(const float *__restrict__ src, double *__restrict__ dst, size_t n)
+{
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = (double)src[i];
+}
+
+// Philox-4x32-10 (Salmon et al. 2011), counter = (point index, env), key = seed.
+__device__ inline void philox_round(uint32_t (&c)[4], uint32_t k0, uint32_t k1)
+{
+    const uint64_t p0 = (uint64_t)0xD2511F53u * c[0];
+    const uint64_t p1 = (uint64_t)0xCD9E8D57u * c[2];
+    const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c[1] ^ k0;
+    const uint32_t n1 = (uint32_t)p1;
+    const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c[3] ^ k1;
+    const uint32_t n3 = (uint32_t)p0;
+    c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+}
+
+// Initial condition of reset() for the envs selected by `mask` (all if nullptr):
+//   u0 != nullptr : u[b,:] = u0[b,:]                     (host-drawn NumPy ICs, parity path)
+//   u0 == nullptr : u[b,i] ~ U(-0.4, 0.4) (kuramoto.py:106), 53-bit uniform from Philox(seed; i, b)
+// also clears the env's non-finite flag and, when there is no burn-in launch, its timestep.
+template <typename T>
+__global__ void reset_rows(T *__restrict__ u, const double *__restrict__ u0, const uint8_t *__restrict__ mask,
+                           uint8_t *__restrict__ nonfinite, int32_t *__restrict__ timestep, int zero_timestep, int B,
+                           int N, uint64_t seed)
+{
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (size_t)B * N) return;
+    const uint32_t env = (uint32_t)(idx / N), pt = (uint32_t)(idx % N);
+    if (mask != nullptr && mask[env] == 0) return;
+    if (u0 != nullptr) {
+        u[idx] = (T)u0[idx];
+    } else {
+        uint32_t c[4] = {pt, env, 0x4b53u /* 'KS' */, 0u};
+        uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+        for (int r = 0; r < 10; ++r) {
+            philox_round(c, k0, k1);
+            k0 += 0x9E3779B9u;
+            k1 += 0xBB67AE85u;
+        }
+        const uint64_t bits = (((uint64_t)c[0] << 32) | c[1]) >> 11;
+        const double r01 = (double)bits * (1.0 / 9007199254740992.0);
+        u[idx] = (T)(-0.4 + 0.8 * r01);
+    }
+    if (pt == 0) {
+        nonfinite[env] = 0;
+        if (zero_timestep) timestep[env] = 0;
+    }
+}
+
+// rhs() and reward on arbitrary states: one warp per row, unmerged stencils in the reference's
+// own order of operations (kuramoto.py:118-129, 64-70).  Memory-bound helper, not the hot path.
+__global__ void eval_rows(int M, int N, double dx, int reward_mode, const double *__restrict__ u,
+                          const float *__restrict__ phi, double *__restrict__ rhs, double *__restrict__ ux_o,
+                          double *__restrict__ uxx_o, double *__restrict__ uxxxx_o, double *__restrict__ reward)
+{
+    const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (row >= M) return;
+    const double *ur = u + (size_t)row * N;
+    const float *pr = phi ? phi + (size_t)row * N : nullptr;
+    const double dx2 = dx * dx, dx4 = dx2 * dx2;
+    const double kUpwind[5] = {-25.0 / 12.0, 4.0, -3.0, 4.0 / 3.0, -1.0 / 4.0};
+    const double kD2[4] = {-49.0 / 18.0, 3.0 / 2.0, -3.0 / 20.0, 1.0 / 90.0};
+    const double kD4[5] = {91.0 / 8.0, -122.0 / 15.0, 169.0 / 60.0, -2.0 / 5.0, 7.0 / 240.0};
+    double s_l2 = 0.0, s_uxx = 0.0, s_ux = 0.0, s_up = 0.0;
+    for (int i = lane; i < N; i += 32) {
+        double v[9];
+#pragma unroll
+        for (int k = -4; k <= 4; ++k) v[k + 4] = ur[(i + k + N) % N];
+        double fwd = kUpwind[0] * (v[4] * v[4]), bwd = -kUpwind[0] * (v[4] * v[4]);
+#pragma unroll
+        for (int k = 1; k <= 4; ++k) {
+            fwd = fwd + kUpwind[k] * (v[4 + k] * v[4 + k]);
+            bwd = bwd - kUpwind[k] * (v[4 - k] * v[4 - k]);
+        }
+        const double ux = (v[4] < 0.0 ? fwd : bwd) / dx;
+        double s2 = kD2[0] * v[4], s4 = kD4[0] * v[4];
+#pragma unroll
+        for (int k = 1; k <= 3; ++k) s2 += kD2[k] * (v[4 + k] + v[4 - k]);
+#pragma unroll
+        for (int k = 1; k <= 4; ++k) s4 += kD4[k] * (v[4 + k] + v[4 - k]);
+        const double uxx = s2 / dx2, uxxxx = s4 / dx4;
+        const double ph = pr ? (double)pr[i] : 0.0;
+        const size_t o = (size_t)row * N + i;
+        if (rhs) rhs[o] = -uxxxx - uxx - 0.5 * ux + ph;
+        if (ux_o) ux_o[o] = ux;
+        if (uxx_o) uxx_o[o] = uxx;
+        if (uxxxx_o) uxxxx_o[o] = uxxxx;
+        s_l2 += v[4] * v[4];
+        s_uxx += uxx * uxx;
+        s_ux += ux * ux;
+        s_up += v[4] * ph;
+    }
+    if (reward) {
+        double t = reward_mode == KS_REWARD_L2 ? s_l2 : (s_uxx + s_ux + s_up);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        if (lane == 0) reward[row] = -(t / N);
+    }
+}
+
+int launch_period(ks_handle *h, int K, const float *actions, const float *phi, float *obs, double *reward,
+                  uint8_t *truncated, int32_t *step, uint8_t *nonfinite_out, int reset_timestep, const uint8_t *mask,
+                  cudaStream_t stream)
+{
+    ks::Params p;
+    p.u = h->u;
+    p.timestep = h->timestep;
+    p.nonfinite = h->nonfinite;
+    p.F = h->F;
+    p.actions = actions;
+    p.phi = phi;
+    p.obs = obs;
+    p.reward = reward;
+    p.truncated = truncated;
+    p.step = step;
+    p.nonfinite_out = nonfinite_out;
+    p.mask = mask;
+    p.B = h->cfg.num_envs;
+    p.N = h->cfg.N;
+    p.J = h->cfg.J;
+    p.K = K;
+    p.cfg_steps = h->cfg.cfg_steps;
+    p.max_episode_steps = h->cfg.max_episode_steps;
+    p.lanes = h->lanes;
+    p.envs_per_warp = h->envs_per_warp;
+    p.reset_timestep = reset_timestep;
+    p.inv_cfg_steps = 1.0 / h->cfg.cfg_steps;
+    p.inv_N = 1.0 / h->cfg.N;
+    void *args[2] = {&p, h->cfg.precision == KS_F64 ? (void *)&h->c64 : (void *)&h->c32};
+    KS_CUDA(h, cudaLaunchKernel(h->kernel, dim3(h->grid), dim3(ks::kBlockThreads), args, 0, stream));
+    h->launches += 1;
+    return KS_OK;
+}
+
+}  // namespace
+
+// =============================================================================================
+// exported C ABI
+// =============================================================================================
+extern "C" {
+
+int ks_abi_version(void) { return KS_ABI_VERSION; }
+
+const char *ks_last_error(const ks_handle *h) { return h ? h->err : g_create_error; }
+
+int ks_create(const ks_config *cfg, ks_handle **out)
+{
+    if (!cfg || !out) return fail(nullptr, KS_ERR_ARG, "ks_create: NULL argument");
+    *out = nullptr;
+    if (cfg->abi_version != KS_ABI_VERSION)
+        return fail(nullptr, KS_ERR_ARG, "ks_create: abi_version %d, library is %d", cfg->abi_version, KS_ABI_VERSION);
+    if (cfg->num_envs < 1 || cfg->N < 9 || cfg->J < 1 || cfg->J > 32 || cfg->cfg_steps < 1 ||
+        cfg->max_episode_steps < 1 || cfg->burnin_periods < 0 || !(cfg->L > 0.0) || !(cfg->dt > 0.0) || !cfg->forcing)
+        return fail(nullptr, KS_ERR_ARG, "ks_create: config out of range (num_envs=%d N=%d J=%d cfg_steps=%d L=%g dt=%g)",
+                    cfg->num_envs, cfg->N, cfg->J, cfg->cfg_steps, cfg->L, cfg->dt);
+    if (cfg->precision != KS_F64 && cfg->precision != KS_F32) return fail(nullptr, KS_ERR_ARG, "ks_create: bad precision");
+    if (cfg->reward_mode != KS_REWARD_L2 && cfg->reward_mode != KS_REWARD_DISSIPATION)
+        return fail(nullptr, KS_ERR_ARG, "ks_create: bad reward_mode");
+
+    int P = cfg->points_per_lane;
+    if (P == 0) P = choose_points_per_lane(cfg->N);
+    if (P < ks::kMinP || P > ks::kMaxP || cfg->N % P || cfg->N / P > 32)
+        return fail(nullptr, KS_ERR_UNSUPPORTED,
+                    "ks_create: N=%d needs N = lanes*P with 4<=P<=16, lanes<=32 (points_per_lane=%d)", cfg->N,
+                    cfg->points_per_lane);
+
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev < 1) {
+        cudaGetLastError();
+        return fail(nullptr, KS_ERR_NO_DEVICE, "ks_create: no CUDA device (%s); this library has no CPU path",
+                    e == cudaSuccess ? "count = 0" : cudaGetErrorString(e));
+    }
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(nullptr, KS_ERR_ARG, "ks_create: device %d of %d", cfg->device, ndev);
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, cfg->device) != cudaSuccess || prop.major != 10)
+        return fail(nullptr, KS_ERR_NO_DEVICE, "ks_create: device %d is sm_%d%d; kernels are built for sm_100a only",
+                    cfg->device, prop.major, prop.minor);
+
+    ks_handle *h = new (std::nothrow) ks_handle();
+    if (!h) return fail(nullptr, KS_ERR_ARG, "ks_create: out of host memory");
+    h->cfg = *cfg;
+    h->cfg.forcing = nullptr;
+    h->cfg.points_per_lane = P;
+    h->P = P;
+    h->lanes = cfg->N / P;
+    h->envs_per_warp = 32 / h->lanes;
+    const long long warps = ((long long)cfg->num_envs + h->envs_per_warp - 1) / h->envs_per_warp;
+    h->grid = (int)((warps * 32 + ks::kBlockThreads - 1) / ks::kBlockThreads);
+    const bool f64 = cfg->precision == KS_F64, l2 = cfg->reward_mode == KS_REWARD_L2;
+    h->kernel = f64 ? (l2 ? ks::period_kernel_f64_l2(P) : ks::period_kernel_f64_diss(P))
+                    : (l2 ? ks::period_kernel_f32_l2(P) : ks::period_kernel_f32_diss(P));
+    const double dx = cfg->L / cfg->N;  // kuramoto.py:55
+    fill_coef(h->c64, dx, cfg->dt);
+    fill_coef(h->c32, dx, cfg->dt);
+
+    DeviceGuard guard(cfg->device);
+    const size_t B = cfg->num_envs, N = cfg->N, J = cfg->J;
+    const size_t esz = f64 ? sizeof(double) : sizeof(float);
+    h->out_off[0] = 0;
+    h->out_off[1] = align16(B * sizeof(double));
+    h->out_off[2] = h->out_off[1] + align16(B * N * sizeof(float));
+    h->out_off[3] = h->out_off[2] + align16(B * sizeof(int32_t));
+    h->out_off[4] = h->out_off[3] + align16(B);
+    h->out_total = h->out_off[4] + align16(B);
+    cudaFuncAttributes attr;
+    int rc = KS_OK;
+    do {
+        if (!guard.ok) { rc = fail(nullptr, KS_ERR_NO_DEVICE, "ks_create: cudaSetDevice(%d) failed", cfg->device); break; }
+#define KS_TRY(call)                                                                  \
+    if ((e = (call)) != cudaSuccess) { rc = cuda_fail(nullptr, e, #call); break; }
+        KS_TRY(cudaFuncGetAttributes(&attr, h->kernel));
+        h->regs = attr.numRegs;
+        KS_TRY(cudaMalloc(&h->u, B * N * esz));
+        KS_TRY(cudaMalloc(&h->timestep, B * sizeof(int32_t)));
+        KS_TRY(cudaMalloc(&h->nonfinite, B));
+        KS_TRY(cudaMalloc(&h->F, J * N * sizeof(float)));
+        KS_TRY(cudaMalloc(&h->actions, B * J * sizeof(float)));
+        KS_TRY(cudaMalloc(&h->out, h->out_total));
+        KS_TRY(cudaMalloc(&h->scratch64, B * N * sizeof(double)));
+        KS_TRY(cudaMalloc(&h->mask, B));
+        KS_TRY(cudaMemset(h->u, 0, B * N * esz));
+        KS_TRY(cudaMemset(h->timestep, 0, B * sizeof(int32_t)));
+        KS_TRY(cudaMemset(h->nonfinite, 0, B));
+        KS_TRY(cudaMemset(h->out, 0, h->out_total));
+        KS_TRY(cudaMemcpy(h->F, cfg->forcing, J * N * sizeof(float), cudaMemcpyHostToDevice));
+#undef KS_TRY
+    } while (0);
+    if (rc != KS_OK) {
+        ks_destroy(h);
+        return rc;
+    }
+    *out = h;
+    return KS_OK;
+}
+
+int ks_destroy(ks_handle *h)
+{
+    if (!h) return KS_OK;
+    {
+        DeviceGuard guard(h->cfg.device);
+        cudaFree(h->u);
+        cudaFree(h->timestep);
+        cudaFree(h->nonfinite);
+        cudaFree(h->F);
+        cudaFree(h->actions);
+        cudaFree(h->out);
+        cudaFree(h->scratch64);
+        cudaFree(h->mask);
+        cudaGetLastError();
+    }
+    delete h;
+    return KS_OK;
+}
+
+int ks_get_config(const ks_handle *h, ks_config *out)
+{
+    if (!h || !out) return KS_ERR_ARG;
+    *out = h->cfg;
+    return KS_OK;
+}
+
+int ks_launch_info(const ks_handle *h, int32_t *P, int32_t *lanes, int32_t *block, int32_t *grid, int32_t *regs)
+{
+    if (!h) return KS_ERR_ARG;
+    if (P) *P = h->P;
+    if (lanes) *lanes = h->lanes;
+    if (block) *block = ks::kBlockThreads;
+    if (grid) *grid = h->grid;
+    if (regs) *regs = h->regs;
+    return KS_OK;
+}
+
+uint64_t ks_launch_count(const ks_handle *h) { return h ? h->launches : 0; }
+
+int ks_out_layout(const ks_handle *h, size_t offsets[5], size_t *total)
+{
+    if (!h) return KS_ERR_ARG;
+    if (offsets) memcpy(offsets, h->out_off, sizeof(h->out_off));
+    if (total) *total = h->out_total;
+    return KS_OK;
+}
+
+int ks_set_state(ks_handle *h, const double *u, const int32_t *timestep, int where, void *stream_)
+{
+    if (!h) return KS_ERR_ARG;
+    if (where != KS_HOST && where != KS_DEVICE) return fail(h, KS_ERR_ARG, "ks_set_state: bad `where`");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    DeviceGuard guard(h->cfg.device);
+    const size_t B = h->cfg.num_envs, n = B * h->cfg.N;
+    const cudaMemcpyKind kind = where == KS_HOST ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
+    if (u) {
+        if (h->cfg.precision == KS_F64) {
+            KS_CUDA(h, cudaMemcpyAsync(h->u, u, n * sizeof(double), kind, stream));
+        } else {
+            const double *src = u;
+            if (where == KS_HOST) {
+                KS_CUDA(h, cudaMemcpyAsync(h->scratch64, u, n * sizeof(double), kind, stream));
+                src = h->scratch64;
+            }
+            convert_f64_to_f32<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(src, (float *)h->u, n);
+            KS_CUDA(h, cudaGetLastError());
+            h->launches += 1;
+        }
+    }
+    if (timestep) KS_CUDA(h, cudaMemcpyAsync(h->timestep, timestep, B * sizeof(int32_t), kind, stream));
+    KS_CUDA(h, cudaMemsetAsync(h->nonfinite, 0, B, stream));
+    if (where == KS_HOST) KS_CUDA(h, cudaStreamSynchronize(stream));  // caller may reuse its host buffers
+    return KS_OK;
+}
+
+int ks_get_state(ks_handle *h, double *u, int32_t *timestep, int where, void *stream_)
+{
+    if (!h) return KS_ERR_ARG;
+    if (where != KS_HOST && where != KS_DEVICE) return fail(h, KS_ERR_ARG, "ks_get_state: bad `where`");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    DeviceGuard guard(h->cfg.device);
+    const size_t B = h->cfg.num_envs, n = B * h->cfg.N;
+    const cudaMemcpyKind kind = where == KS_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
+    if (u) {
+        if (h->cfg.precision == KS_F64) {
+            KS_CUDA(h, cudaMemcpyAsync(u, h->u, n * sizeof(double), kind, stream));
+        } else {
+            double *dst = where == KS_HOST ? h->scratch64 : u;
+            convert_f32_to_f64<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>((const float *)h->u, dst, n);
+            KS_CUDA(h, cudaGetLastError());
+            h->launches += 1;
+            if (where == KS_HOST) KS_CUDA(h, cudaMemcpyAsync(u, h->scratch64, n * sizeof(double), kind, stream));
+        }
+    }
+    if (timestep) KS_CUDA(h, cudaMemcpyAsync(timestep, h->timestep, B * sizeof(int32_t), kind, stream));
+    if (where == KS_HOST) KS_CUDA(h, cudaStreamSynchronize(stream));
+    return KS_OK;
+}
+
+int ks_reset(ks_handle *h, const double *u0, const uint8_t *mask, int where, uint64_t seed,
+             int32_t burnin_periods, void *stream_)
+{
+    if (!h) return KS_ERR_ARG;
+    if (where != KS_HOST && where != KS_DEVICE) return fail(h, KS_ERR_ARG, "ks_reset: bad `where`");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    DeviceGuard guard(h->cfg.device);
+    const size_t B = h->cfg.num_envs, n = B * h->cfg.N;
+    const double *u0_dev = u0;
+    const uint8_t *mask_dev = mask;
+    if (where == KS_HOST) {
+        if (u0) {
+            KS_CUDA(h, cudaMemcpyAsync(h->scratch64, u0, n * sizeof(double), cudaMemcpyHostToDevice, stream));
+            u0_dev = h->scratch64;
+        }
+        if (mask) {
+            KS_CUDA(h, cudaMemcpyAsync(h->mask, mask, B, cudaMemcpyHostToDevice, stream));
+            mask_dev = h->mask;
+        }
+    }
+    const int K = burnin_periods < 0 ? h->cfg.burnin_periods : burnin_periods;
+    const unsigned blocks = (unsigned)((n + 255) / 256);
+    if (h->cfg.precision == KS_F64)
+        reset_rows<double><<<blocks, 256, 0, stream>>>((double *)h->u, u0_dev, mask_dev, h->nonfinite, h->timestep,
+                                                       K == 0, (int)B, h->cfg.N, seed);
+    else
+        reset_rows<float><<<blocks, 256, 0, stream>>>((float *)h->u, u0_dev, mask_dev, h->nonfinite, h->timestep,
+                                                      K == 0, (int)B, h->cfg.N, seed);
+    KS_CUDA(h, cudaGetLastError());
+    h->launches += 1;
+    int rc = KS_OK;
+    if (K > 0) rc = launch_period(h, K, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 1, mask_dev, stream);
+    // host buffers (u0 / mask) may be reused by the caller as soon as we return
+    if (rc == KS_OK && where == KS_HOST && (u0 || mask)) KS_CUDA(h, cudaStreamSynchronize(stream));
+    return rc;
+}
+
+int ks_step(ks_handle *h, const float *actions, const float *phi, float *obs, double *reward, uint8_t *truncated,
+            int32_t *step, uint8_t *nonfinite, void *stream)
+{
+    if (!h) return KS_ERR_ARG;
+    if (!actions && !phi) return fail(h, KS_ERR_ARG, "ks_step: need actions or phi");
+    DeviceGuard guard(h->cfg.device);
+    return launch_period(h, 1, actions, phi, obs, reward, truncated, step, nonfinite, 0, nullptr, (cudaStream_t)stream);
+}
+
+int ks_rollout(ks_handle *h, int32_t K, const float *actions, float *obs, double *reward, uint8_t *truncated,
+               int32_t *step, uint8_t *nonfinite, void *stream)
+{
+    if (!h) return KS_ERR_ARG;
+    if (K < 1) return fail(h, KS_ERR_ARG, "ks_rollout: K = %d", K);
+    DeviceGuard guard(h->cfg.device);
+    return launch_period(h, K, actions, nullptr, obs, reward, truncated, step, nonfinite, 0, nullptr, (cudaStream_t)stream);
+}
+
+int ks_step_host(ks_handle *h, const float *actions_host, void *out_host, void *stream_)
+{
+    if (!h || !actions_host || !out_host) return h ? fail(h, KS_ERR_ARG, "ks_step_host: NULL argument") : KS_ERR_ARG;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    DeviceGuard guard(h->cfg.device);
+    const size_t B = h->cfg.num_envs;
+    KS_CUDA(h, cudaMemcpyAsync(h->actions, actions_host, B * h->cfg.J * sizeof(float), cudaMemcpyHostToDevice, stream));
+    int rc = launch_period(h, 1, h->actions, nullptr, (float *)(h->out + h->out_off[1]), (double *)(h->out + h->out_off[0]),
+                           h->out + h->out_off[3], (int32_t *)(h->out + h->out_off[2]), h->out + h->out_off[4], 0, nullptr, stream);
+    if (rc != KS_OK) return rc;
+    KS_CUDA(h, cudaMemcpyAsync(out_host, h->out, h->out_total, cudaMemcpyDeviceToHost, stream));
+    KS_CUDA(h, cudaStreamSynchronize(stream));
+    return KS_OK;
+}
+
+int ks_status(ks_handle *h, uint8_t *nonfinite_host, int32_t *any, void *stream_)
+{
+    if (!h) return KS_ERR_ARG;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    DeviceGuard guard(h->cfg.device);
+    const size_t B = h->cfg.num_envs;
+    uint8_t *tmp = nonfinite_host;
+    if (!tmp) {
+        tmp = new (std::nothrow) uint8_t[B];
+        if (!tmp) return fail(h, KS_ERR_ARG, "ks_status: out of host memory");
+    }
+    cudaError_t e = cudaMemcpyAsync(tmp, h->nonfinite, B, cudaMemcpyDeviceToHost, stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+    int32_t acc = 0;
+    if (e == cudaSuccess)
+        for (size_t i = 0; i < B; ++i) acc |= tmp[i];
+    if (!nonfinite_host) delete[] tmp;
+    if (e != cudaSuccess) return cuda_fail(h, e, "ks_status copy");
+    if (any) *any = acc ? 1 : 0;
+    return KS_OK;
+}
+
+int ks_eval(ks_handle *h, int32_t M, const double *u, const float *phi, double *rhs, double *ux, double *uxx,
+            double *uxxxx, double *reward, void *stream)
+{
+    if (!h || !u || M < 0) return h ? fail(h, KS_ERR_ARG, "ks_eval: bad argument") : KS_ERR_ARG;
+    if (M == 0) return KS_OK;
+    DeviceGuard guard(h->cfg.device);
+    const double dx = h->cfg.L / h->cfg.N;
+    const unsigned blocks = (unsigned)(((size_t)M * 32 + 127) / 128);
+    eval_rows<<<blocks, 128, 0, (cudaStream_t)stream>>>(M, h->cfg.N, dx, h->cfg.reward_mode, u, phi, rhs, ux, uxx,
+                                                        uxxxx, reward);
+    KS_CUDA(h, cudaGetLastError());
+    h->launches += 1;
+    return KS_OK;
+}
+
+}  // extern "C"

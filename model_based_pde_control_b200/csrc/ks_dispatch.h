@@ -1,0 +1,39 @@
+// ks_dispatch.h -- kernel lookup shared by the instantiation units and the C-ABI layer.
+#pragma once
+#include "ks_kernels.cuh"
+
+namespace ks {
+
+constexpr int kMinP = 4;
+constexpr int kMaxP = 16;
+
+// One translation unit per (precision, reward mode) so that the units compile in parallel.
+// Each returns the __global__ function for `P` points per lane, or nullptr if P is out of range.
+const void *period_kernel_f64_l2(int P);
+const void *period_kernel_f64_diss(int P);
+const void *period_kernel_f32_l2(int P);
+const void *period_kernel_f32_diss(int P);
+
+}  // namespace ks
+
+// Expands to the switch over every supported P for one (T, RMODE) pair.
+#define KS_DEFINE_PERIOD_LOOKUP(NAME, T, RMODE)                                              \
+    const void *ks::NAME(int P)                                                              \
+    {                                                                                        \
+        switch (P) {                                                                         \
+            case 4: return (const void *)&ks::ks_period_kernel<T, 4, RMODE>;                 \
+            case 5: return (const void *)&ks::ks_period_kernel<T, 5, RMODE>;                 \
+            case 6: return (const void *)&ks::ks_period_kernel<T, 6, RMODE>;                 \
+            case 7: return (const void *)&ks::ks_period_kernel<T, 7, RMODE>;                 \
+            case 8: return (const void *)&ks::ks_period_kernel<T, 8, RMODE>;                 \
+            case 9: return (const void *)&ks::ks_period_kernel<T, 9, RMODE>;                 \
+            case 10: return (const void *)&ks::ks_period_kernel<T, 10, RMODE>;               \
+            case 11: return (const void *)&ks::ks_period_kernel<T, 11, RMODE>;               \
+            case 12: return (const void *)&ks::ks_period_kernel<T, 12, RMODE>;               \
+            case 13: return (const void *)&ks::ks_period_kernel<T, 13, RMODE>;               \
+            case 14: return (const void *)&ks::ks_period_kernel<T, 14, RMODE>;               \
+            case 15: return (const void *)&ks::ks_period_kernel<T, 15, RMODE>;               \
+            case 16: return (const void *)&ks::ks_period_kernel<T, 16, RMODE>;               \
+            default: return nullptr;                                                         \
+        }                                                                                    \
+    }

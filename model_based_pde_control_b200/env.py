@@ -1,0 +1,441 @@
+"""``KSVecEnv`` -- GPU-resident vectorised drop-in for ``KuramotoSivashinskyEnv-v0``.
+
+Host-side mirror of the reference's env interface over the C ABI of ``libks_b200.so``:
+
+* constructor kwargs, attributes and helper objects of the single env
+  (``pdegym/kuramoto/kuramoto.py:29-76,131-150``): ``L, N, cfg_steps, Tmax, dt, sigma, dx, x,
+  max_episode_steps, forcing, noop, reward_func, rhs, scenario, time``;
+* the gym 0.25.2 vector-env protocol as the reference consumes it
+  (``pdecontrol/mbrl/mbrl.py:81-86``, ``pdegym/common/vec_wrappers.py``,
+  ``pdecontrol/mbrl/worker.py:48-88``): ``reset``, ``step_async`` / ``step_wait`` / ``step``
+  returning ``obs (B,1,N) float32``, ``rewards (B,) float64``, ``terminated`` (always False),
+  ``truncated``, ``infos`` with ``"step"`` and -- on the truncation step -- ``"final_observation"``
+  / ``"_final_observation"``, followed by the auto-reset (burn-in of 800 no-op periods);
+* a device-tensor API (``step_device`` / ``rollout_device``) for policies that live on the GPU.
+
+All numerics run in the CUDA kernels; nothing here computes the PDE on the CPU.
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+import os
+from typing import Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib
+from .forcing import GaussianForcing
+from .spaces import Box, VectorEnvBase
+
+BURNIN_TIME = 200.0    # kuramoto.py:103
+IC_AMPLITUDE = 0.4     # kuramoto.py:106
+DEFAULT_XI = (0.0, 0.25, 0.5, 0.75)   # kuramoto.py:18
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+class KSVecEnv(VectorEnvBase):
+    """``num_envs`` independent Kuramoto-Sivashinsky control environments on one B200.
+
+    Parameters mirror ``KuramotoSivashinskyEnv.__init__`` (``config`` dict or keywords) plus:
+
+    ``Xi``            relative jet positions (a class attribute in the reference, kuramoto.py:18)
+    ``device``        CUDA device ordinal (default: ``LOCAL_RANK`` or the current device)
+    ``precision``     ``"f64"`` (parity mode, default) or ``"f32"``
+    ``reward_mode``   ``"l2"`` / ``"dissipation"``; default follows the reference's selector
+                      ``l2control if self.objective else dissipation`` (kuramoto.py:72), i.e. any
+                      non-empty ``objective`` string -- including the default ``"dissipation"`` --
+                      selects the L2 reward
+    ``ic``            ``"numpy"``: ``reset(seed=s)`` draws env ``i``'s initial condition on the host
+                      exactly like ``np.random.seed(s+i); np.random.uniform(-0.4,0.4,N)``;
+                      ``"device"``: counter-based Philox on the GPU.  ``reset(seed=None)`` and
+                      auto-resets always use the device generator with a fresh OS seed (the
+                      reference reseeds from OS entropy there, kuramoto.py:101).
+    ``burnin_periods`` override of ``int(200/dt/cfg_steps)`` (= 800) no-op periods in ``reset``
+    """
+
+    metadata = {"render.modes": ["rgb_array"]}
+    reward_range = (-float("inf"), float("inf"))
+    eps = np.finfo(np.float32).eps
+
+    def __init__(self, num_envs: int, config: Optional[dict] = None, *, Xi: Optional[Sequence[float]] = None,
+                 device: Optional[int] = None, precision: str = "f64", reward_mode: Optional[str] = None,
+                 ic: str = "numpy", burnin_periods: Optional[int] = None, points_per_lane: int = 0,
+                 copy: bool = True, **kwargs):
+        cfg = dict(config or {})
+        cfg.update(kwargs)
+        self.L = float(cfg.pop("L", 22.0))
+        self.N = int(cfg.pop("N", 64))
+        self.cfg_steps = int(cfg.pop("cfg_steps", 250))
+        self.Ttrans = cfg.pop("Ttrans", 40)
+        self.Tmax = float(cfg.pop("Tmax", 100.0))
+        self.dt = float(cfg.pop("dt", 0.001))
+        self.noise = cfg.pop("noise", 0.1)
+        self.sigma = float(cfg.pop("sigma", 0.4))
+        self.lmbda = cfg.pop("lmbda", 0.0)
+        self.objective = cfg.pop("objective", "dissipation")
+        if cfg:
+            raise TypeError(f"unexpected config keys: {sorted(cfg)}")
+        self.Xi = list(DEFAULT_XI if Xi is None else Xi)
+        if reward_mode is None:
+            reward_mode = "l2" if self.objective else "dissipation"     # kuramoto.py:72
+        if reward_mode not in _lib.REWARD_MODES:
+            raise ValueError(f"reward_mode must be one of {sorted(_lib.REWARD_MODES)}")
+        if precision not in _lib.PRECISIONS:
+            raise ValueError(f"precision must be one of {sorted(_lib.PRECISIONS)}")
+        if ic not in ("numpy", "device"):
+            raise ValueError("ic must be 'numpy' or 'device'")
+        self.reward_mode, self.precision, self.ic, self.copy = reward_mode, precision, ic, copy
+
+        self.dx = self.L / self.N                                                         # :55
+        self.x = np.linspace(0.0, self.L - self.L / self.N, self.N, dtype=np.float32)     # :56
+        self.max_episode_steps = math.ceil(self.Tmax / (self.dt * self.cfg_steps))        # :57
+        self.burnin_periods = int(BURNIN_TIME / self.dt / self.cfg_steps) if burnin_periods is None \
+            else int(burnin_periods)                                                      # :103
+        self.forcing = GaussianForcing(self.x, self.Xi, self.sigma, self.L, self.N)       # :60
+        self.J = self.forcing.J
+        self.noop = np.zeros((1, self.J), dtype=np.float32)                               # :62
+
+        single_action = Box(-1.0, 1.0, shape=(1, self.J), dtype=np.float32)               # :75
+        single_obs = Box(-np.inf, np.inf, shape=(1, self.N), dtype=np.float32)            # :76
+        super().__init__(num_envs, single_obs, single_action)
+
+        # ---- the CUDA side: fails loudly without the built library / a B200 ----
+        lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise RuntimeError("KSVecEnv needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+        if device is None:
+            device = int(os.environ.get("LOCAL_RANK", torch.cuda.current_device()))
+        self.device_index = int(device)
+        self.device = torch.device("cuda", self.device_index)
+        self._F_host = self.forcing.matrix()
+        c = _lib.KsConfig(
+            abi_version=_lib.KS_ABI_VERSION, num_envs=num_envs, N=self.N, J=self.J, cfg_steps=self.cfg_steps,
+            max_episode_steps=self.max_episode_steps, burnin_periods=self.burnin_periods,
+            precision=_lib.PRECISIONS[precision], reward_mode=_lib.REWARD_MODES[reward_mode],
+            device=self.device_index, points_per_lane=points_per_lane, reserved=0, L=self.L, dt=self.dt,
+            forcing=self._F_host.ctypes.data)
+        handle = ctypes.c_void_p()
+        torch.cuda.init()
+        _lib.check(None, lib.ks_create(ctypes.byref(c), ctypes.byref(handle)))
+        self._lib, self._h = lib, handle
+
+        offs = _lib._SIZE5()
+        total = ctypes.c_size_t()
+        _lib.check(self._h, lib.ks_out_layout(self._h, ctypes.byref(offs), ctypes.byref(total)))
+        B, N = num_envs, self.N
+        self._out_pinned = torch.empty(total.value, dtype=torch.uint8, pin_memory=True)
+        host = self._out_pinned.numpy()
+        self._h_reward = host[offs[0]:offs[0] + 8 * B].view(np.float64)
+        self._h_obs = host[offs[1]:offs[1] + 4 * B * N].view(np.float32).reshape(B, 1, N)
+        self._h_step = host[offs[2]:offs[2] + 4 * B].view(np.int32)
+        self._h_trunc = host[offs[3]:offs[3] + B].view(np.uint8)
+        self._h_bad = host[offs[4]:offs[4] + B].view(np.uint8)
+        self._act_pinned = torch.empty((B, self.J), dtype=torch.float32, pin_memory=True)
+        self._h_act = self._act_pinned.numpy()
+        # device-side outputs of the tensor API (allocated on first use)
+        self._d_out = None
+        self._pending_actions = None
+        self.h2d_bytes_per_step = B * self.J * 4
+        self.d2h_bytes_per_step = int(total.value)
+
+    # ------------------------------------------------------------------ helpers
+    def _stream(self):
+        return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _check_open(self):
+        if self._h is None:
+            raise RuntimeError("KSVecEnv is closed")
+
+    @property
+    def launch_count(self) -> int:
+        """Number of CUDA kernels launched through this env's handle so far."""
+        return int(self._lib.ks_launch_count(self._h))
+
+    def launch_info(self) -> dict:
+        v = [ctypes.c_int32() for _ in range(5)]
+        _lib.check(self._h, self._lib.ks_launch_info(self._h, *[ctypes.byref(x) for x in v]))
+        keys = ("points_per_lane", "lanes_per_env", "block_threads", "grid_blocks", "regs_per_thread")
+        return {k: x.value for k, x in zip(keys, v)}
+
+    @property
+    def time(self) -> np.ndarray:
+        """Physical time per env, ``timestep * cfg_steps * dt`` (kuramoto.py:131-133)."""
+        return self.get_state()[1] * self.cfg_steps * self.dt
+
+    @property
+    def scenario(self) -> dict:
+        """kuramoto.py:135-150, including its hard-coded ``noise`` / ``lmbda`` entries."""
+        return {"cfg_steps": self.cfg_steps, "Ttrans": self.Ttrans, "L": self.L, "N": self.N, "dx": self.dx,
+                "Tmax": self.Tmax, "dt": self.dt, "Xi": self.Xi, "noise": 0.1, "lmbda": 1.0,
+                "objective": self.objective}
+
+    # ------------------------------------------------------------------ state access
+    def set_state(self, u, timestep=None) -> None:
+        """``env.u = u; env.timestep = t`` for every env.  ``u``: ``[B,N]`` float64 array / tensor."""
+        self._check_open()
+        B, N = self.num_envs, self.N
+        ts_arr = None
+        if timestep is not None:
+            ts_arr = np.ascontiguousarray(np.broadcast_to(np.asarray(timestep, dtype=np.int32), (B,)))
+        if isinstance(u, torch.Tensor) and u.is_cuda:
+            ud = u.to(device=self.device, dtype=torch.float64).reshape(B, N).contiguous()
+            _lib.check(self._h, self._lib.ks_set_state(self._h, _ptr(ud), None, _lib.KS_DEVICE, self._stream()))
+            if ts_arr is not None:
+                _lib.check(self._h, self._lib.ks_set_state(self._h, None, ts_arr.ctypes.data, _lib.KS_HOST,
+                                                           self._stream()))
+            return
+        ua = None
+        if u is not None:
+            ua = np.ascontiguousarray(np.asarray(u, dtype=np.float64).reshape(B, N))
+        _lib.check(self._h, self._lib.ks_set_state(
+            self._h, None if ua is None else ua.ctypes.data, None if ts_arr is None else ts_arr.ctypes.data,
+            _lib.KS_HOST, self._stream()))
+
+    def get_state(self):
+        """``(u [B,N] float64, timestep [B] int32)`` as NumPy arrays (synchronises)."""
+        self._check_open()
+        u = np.empty((self.num_envs, self.N), dtype=np.float64)
+        ts = np.empty(self.num_envs, dtype=np.int32)
+        _lib.check(self._h, self._lib.ks_get_state(self._h, u.ctypes.data, ts.ctypes.data, _lib.KS_HOST,
+                                                   self._stream()))
+        return u, ts
+
+    def get_state_device(self):
+        """``(u [B,N] float64, timestep [B] int32)`` as CUDA tensors (stream-ordered, no sync)."""
+        self._check_open()
+        u = torch.empty((self.num_envs, self.N), dtype=torch.float64, device=self.device)
+        ts = torch.empty(self.num_envs, dtype=torch.int32, device=self.device)
+        _lib.check(self._h, self._lib.ks_get_state(self._h, _ptr(u), _ptr(ts), _lib.KS_DEVICE, self._stream()))
+        return u, ts
+
+    # ------------------------------------------------------------------ reset
+    def initial_conditions(self, seed: Optional[int], mask: Optional[np.ndarray] = None) -> np.ndarray:
+        """Host draws of ``reset``'s initial condition: env ``i`` uses the legacy MT19937 stream of
+        ``np.random.seed(seed + i)`` (gym 0.25.2 seeds sub-env ``i`` with ``seed + i``), then
+        ``uniform(-0.4, 0.4, N)`` (kuramoto.py:101,106)."""
+        u0 = np.zeros((self.num_envs, self.N), dtype=np.float64)
+        for i in range(self.num_envs):
+            if mask is not None and not mask[i]:
+                continue
+            rs = np.random.RandomState(None if seed is None else seed + i)
+            u0[i] = rs.uniform(-IC_AMPLITUDE, IC_AMPLITUDE, size=self.N)
+        return u0
+
+    def _reset_impl(self, seed, u0, mask, burnin_periods):
+        mask_arr = None
+        if mask is not None:
+            mask_arr = np.ascontiguousarray(np.asarray(mask, dtype=bool).astype(np.uint8))
+        K = -1 if burnin_periods is None else int(burnin_periods)
+        if u0 is None and self.ic == "numpy" and seed is not None:
+            u0 = self.initial_conditions(seed, mask_arr)
+        if u0 is not None:
+            u0 = np.ascontiguousarray(np.asarray(u0, dtype=np.float64).reshape(self.num_envs, self.N))
+            _lib.check(self._h, self._lib.ks_reset(
+                self._h, u0.ctypes.data, None if mask_arr is None else mask_arr.ctypes.data, _lib.KS_HOST, 0, K,
+                self._stream()))
+        else:
+            dev_seed = int.from_bytes(os.urandom(8), "little") if seed is None else int(seed) & (2 ** 64 - 1)
+            _lib.check(self._h, self._lib.ks_reset(
+                self._h, None, None if mask_arr is None else mask_arr.ctypes.data, _lib.KS_HOST, dev_seed, K,
+                self._stream()))
+
+    def reset(self, seed: Optional[int] = None, return_info: bool = False, options: Optional[dict] = None,
+              *, u0=None, burnin_periods: Optional[int] = None, **kwargs):
+        """``KuramotoSivashinskyEnv.reset`` for every env (kuramoto.py:100-116): initial condition,
+        ``burnin_periods`` no-op control periods in one launch, ``timestep = 0``.
+
+        Returns ``obs (B,1,N) float32`` (and ``{"step": zeros}`` when ``return_info``).  ``u0``
+        injects initial conditions (``[B,N]`` float64) instead of drawing them.
+        """
+        self._check_open()
+        self._pending_actions = None
+        self._reset_impl(seed, u0, None, burnin_periods)
+        u, ts = self.get_state()
+        self._raise_if_nonfinite(u)
+        obs = u.astype(np.float32).reshape(self.num_envs, 1, self.N)
+        if return_info:
+            return obs, {"step": ts.astype(np.int64), "_step": np.ones(self.num_envs, dtype=bool)}
+        return obs
+
+    # ------------------------------------------------------------------ step (host / NumPy API)
+    def step_async(self, actions) -> None:
+        """Stage actions ``(B,1,J)`` / ``(B,J)`` as float32 (``np.array(action, float32)``, :79)."""
+        self._check_open()
+        a = np.asarray(actions, dtype=np.float32)
+        if a.size != self.num_envs * self.J:
+            raise ValueError(f"actions have shape {a.shape}, expected ({self.num_envs}, 1, {self.J})")
+        np.copyto(self._h_act, a.reshape(self.num_envs, self.J))
+        self._pending_actions = True
+
+    def step_wait(self, **kwargs):
+        """One control period for every env; H2D of the actions, one kernel, one D2H of the packed
+        outputs.  Envs whose episode ends are reset (800-period burn-in) before returning, with the
+        pre-reset observation in ``infos["final_observation"]`` as gym 0.25.2 does."""
+        self._check_open()
+        if not self._pending_actions:
+            raise RuntimeError("step_wait() called without step_async()")
+        self._pending_actions = None
+        _lib.check(self._h, self._lib.ks_step_host(self._h, self._h_act.ctypes.data,
+                                                   self._out_pinned.data_ptr(), self._stream()))
+        if self._h_bad.any():
+            bad = np.nonzero(self._h_bad)[0]
+            raise FloatingPointError(f"overflow encountered in KS state of env(s) {bad[:8].tolist()}"
+                                     f"{'...' if bad.size > 8 else ''} (np.seterr(over='raise') in the reference)")
+        copy = np.array if self.copy else np.asarray
+        obs = copy(self._h_obs)
+        rewards = copy(self._h_reward)
+        steps = self._h_step.astype(np.int64)
+        truncated = self._h_trunc.astype(bool)
+        terminated = np.zeros(self.num_envs, dtype=bool)
+        infos = {"step": steps, "_step": np.ones(self.num_envs, dtype=bool)}
+        if truncated.any():
+            # gym 0.25.2 vector-env auto-reset: final obs is the single env's float64 (1,N) array
+            u, _ = self.get_state()
+            finals = np.empty(self.num_envs, dtype=object)
+            for i in np.nonzero(truncated)[0]:
+                finals[i] = u[i].reshape(1, self.N)
+            infos["final_observation"] = finals
+            infos["_final_observation"] = truncated.copy()
+            self._reset_impl(None, None, None if truncated.all() else truncated, None)
+            u_new, _ = self.get_state()
+            obs = np.array(obs)
+            obs[truncated] = u_new[truncated].astype(np.float32).reshape(-1, 1, self.N)
+        return obs, rewards, terminated, truncated, infos
+
+    def step(self, actions):
+        self.step_async(actions)
+        return self.step_wait()
+
+    def _raise_if_nonfinite(self, u):
+        if not np.all(np.isfinite(u)):
+            raise FloatingPointError("overflow encountered in KS state")
+
+    # ------------------------------------------------------------------ device-tensor API
+    def _device_outputs(self, K: int):
+        key = K
+        if self._d_out is None or self._d_out[0] != key:
+            B, N, dev = self.num_envs, self.N, self.device
+            lead = (B,) if K == 0 else (K, B)
+            self._d_out = (key, dict(
+                obs=torch.empty(lead + (N,), dtype=torch.float32, device=dev),
+                reward=torch.empty(lead, dtype=torch.float64, device=dev),
+                truncated=torch.empty(lead, dtype=torch.uint8, device=dev),
+                step=torch.empty(lead, dtype=torch.int32, device=dev),
+                nonfinite=torch.empty(lead, dtype=torch.uint8, device=dev)))
+        return self._d_out[1]
+
+    def step_device(self, actions: torch.Tensor, phi: Optional[torch.Tensor] = None) -> dict:
+        """One control period with device-resident inputs and outputs; asynchronous on the current
+        stream, no host synchronisation, no auto-reset.  ``actions``: CUDA float32 ``[B,J]`` (or
+        ``[B,1,J]``).  ``phi`` (CUDA float32 ``[B,N]``) overrides the in-kernel ``a @ F``.
+        Returns a dict of CUDA tensors that are REUSED by the next call:
+        ``obs [B,N] f32, reward [B] f64, truncated [B] u8, step [B] i32, nonfinite [B] u8``."""
+        self._check_open()
+        out = self._device_outputs(0)
+        a = None
+        if actions is not None:
+            a = actions.to(device=self.device, dtype=torch.float32).reshape(self.num_envs, self.J).contiguous()
+        p = None
+        if phi is not None:
+            p = phi.to(device=self.device, dtype=torch.float32).reshape(self.num_envs, self.N).contiguous()
+        _lib.check(self._h, self._lib.ks_step(self._h, _ptr(a), _ptr(p), _ptr(out["obs"]), _ptr(out["reward"]),
+                                              _ptr(out["truncated"]), _ptr(out["step"]), _ptr(out["nonfinite"]),
+                                              self._stream()))
+        return out
+
+    def rollout_device(self, actions: Optional[torch.Tensor], K: Optional[int] = None, outputs: bool = True) -> dict:
+        """``K`` control periods in ONE persistent launch (open loop).  ``actions``: CUDA float32
+        ``[K,B,J]`` or ``None`` for no-op periods (then ``K`` is required)."""
+        self._check_open()
+        a = None
+        if actions is not None:
+            a = actions.to(device=self.device, dtype=torch.float32).reshape(-1, self.num_envs, self.J).contiguous()
+            K = int(a.shape[0])
+        if not K or K < 1:
+            raise ValueError("K >= 1 required")
+        out = self._device_outputs(K) if outputs else dict(obs=None, reward=None, truncated=None, step=None,
+                                                           nonfinite=None)
+        _lib.check(self._h, self._lib.ks_rollout(self._h, K, _ptr(a), _ptr(out["obs"]), _ptr(out["reward"]),
+                                                 _ptr(out["truncated"]), _ptr(out["step"]), _ptr(out["nonfinite"]),
+                                                 self._stream()))
+        return out
+
+    def reset_device(self, seed: Optional[int] = None, mask: Optional[torch.Tensor] = None,
+                     burnin_periods: Optional[int] = None) -> None:
+        """Stream-ordered reset with device-generated initial conditions (no host sync)."""
+        self._check_open()
+        dev_seed = int.from_bytes(os.urandom(8), "little") if seed is None else int(seed) & (2 ** 64 - 1)
+        m = None if mask is None else mask.to(device=self.device, dtype=torch.uint8).contiguous()
+        K = -1 if burnin_periods is None else int(burnin_periods)
+        _lib.check(self._h, self._lib.ks_reset(self._h, None, _ptr(m), _lib.KS_DEVICE, dev_seed, K, self._stream()))
+
+    def nonfinite(self) -> np.ndarray:
+        """Sticky per-env blow-up flags (the reference raises ``FloatingPointError`` instead)."""
+        self._check_open()
+        flags = np.empty(self.num_envs, dtype=np.uint8)
+        _lib.check(self._h, self._lib.ks_status(self._h, flags.ctypes.data, None, self._stream()))
+        return flags.astype(bool)
+
+    # ------------------------------------------------------------------ env.rhs / env.reward_func
+    def evaluate(self, u, phi=None, want=("rhs", "ux", "uxx", "uxxxx", "reward")) -> dict:
+        """Batched ``rhs`` / derivative triple / reward of arbitrary states on the GPU
+        (kuramoto.py:118-129, 64-70).  ``u [M,N]`` float64, ``phi [M,N]`` float32 or None."""
+        self._check_open()
+        is_np = not isinstance(u, torch.Tensor)
+        ud = torch.as_tensor(np.asarray(u, dtype=np.float64) if is_np else u).to(self.device, torch.float64)
+        ud = ud.reshape(-1, self.N).contiguous()
+        M = ud.shape[0]
+        pd = None
+        if phi is not None:
+            pd = torch.as_tensor(np.asarray(phi, dtype=np.float32) if not isinstance(phi, torch.Tensor) else phi)
+            pd = pd.to(self.device, torch.float32).broadcast_to(ud.shape).contiguous()
+        bufs = {k: torch.empty((M, self.N) if k != "reward" else (M,), dtype=torch.float64, device=self.device)
+                for k in want}
+        _lib.check(self._h, self._lib.ks_eval(self._h, M, _ptr(ud), _ptr(pd), _ptr(bufs.get("rhs")),
+                                              _ptr(bufs.get("ux")), _ptr(bufs.get("uxx")), _ptr(bufs.get("uxxxx")),
+                                              _ptr(bufs.get("reward")), self._stream()))
+        if is_np:
+            return {k: v.cpu().numpy() for k, v in bufs.items()}
+        return bufs
+
+    def rhs(self, u, phi):
+        """``env.rhs(u, phi)`` -> ``(rhs, (ux, uxx, uxxxx))`` for one state or a batch (GPU)."""
+        shape = np.shape(u) if not isinstance(u, torch.Tensor) else tuple(u.shape)
+        r = self.evaluate(u, phi, want=("rhs", "ux", "uxx", "uxxxx"))
+        rs = lambda a: a.reshape(shape)  # noqa: E731
+        return rs(r["rhs"]), (rs(r["ux"]), rs(r["uxx"]), rs(r["uxxxx"]))
+
+    def reward_func(self, obs, phi=None, *args, **kwargs):
+        """``env.reward_func(obs, phi)`` (FuncTransform over ``l2control`` / ``dissipation``,
+        kuramoto.py:64-73) for one observation ``(1,N)`` / ``(N,)`` -> scalar, or a batch
+        ``[M,(1,)N]`` -> ``[M]``; evaluated by the CUDA ``ks_eval`` kernel."""
+        is_np = not isinstance(obs, torch.Tensor)
+        o = np.asarray(obs, dtype=np.float64) if is_np else obs.to(torch.float64)
+        single = o.size == self.N if is_np else o.numel() == self.N
+        if self.reward_mode == "dissipation" and phi is None:
+            raise TypeError("dissipation reward needs phi")
+        r = self.evaluate(o.reshape(-1, self.N), None if phi is None else
+                          (np.asarray(phi, dtype=np.float32).reshape(-1, self.N) if not isinstance(phi, torch.Tensor)
+                           else phi.reshape(-1, self.N)), want=("reward",))["reward"]
+        return r[0] if single else r
+
+    # ------------------------------------------------------------------ teardown
+    def close_extras(self, **kwargs):
+        if getattr(self, "_h", None) is not None:
+            self._lib.ks_destroy(self._h)
+            self._h = None
+
+    def close(self, **kwargs):
+        self.close_extras(**kwargs)
+        self.closed = True
+
+    def __del__(self):
+        try:
+            self.close_extras()
+        except Exception:
+            pass

@@ -1,0 +1,107 @@
+"""Env sharding across GPUs: one process and one ``ks_handle`` per GPU, contiguous env ranges.
+
+Every environment is independent, so the solver needs no exchange; the only collective is the
+all-gather of observations / rewards / flags after each control period so that every learner rank
+sees the whole batch.  The reference has no counterpart: it runs one
+process per env through gym's ``AsyncVectorEnv`` (``pdecontrol/mbrl/mbrl.py:81-86``).
+
+The sharding arithmetic and the gather layout are backend-agnostic (they work on CPU tensors
+over ``gloo``, which is how they are unit-tested); the env itself needs CUDA.
+"""
+from __future__ import annotations
+
+from typing import Callable, Optional
+
+import torch
+import torch.distributed as dist
+
+
+def shard_range(num_envs: int, rank: int, world_size: int) -> tuple[int, int]:
+    """Contiguous ``[lo, hi)`` env range of ``rank``; the first ``num_envs % world_size`` ranks
+    get one extra env.  ``world_size`` divides 4096 / 65536 in all BASELINE configs."""
+    if not (0 <= rank < world_size):
+        raise ValueError(f"rank {rank} outside world of {world_size}")
+    base, extra = divmod(num_envs, world_size)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def gather_batch(local: dict, num_envs: int, group=None) -> dict:
+    """All-gather per-env tensors (leading dim = local envs) into full-batch tensors, rank order
+    = env order.  Equal shards use ``all_gather_into_tensor`` (one NCCL all-gather per tensor);
+    ragged shards fall back to ``all_gather`` on padded buffers."""
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    sizes = [shard_range(num_envs, r, world)[1] - shard_range(num_envs, r, world)[0] for r in range(world)]
+    out = {}
+    for key, t in local.items():
+        if t is None:
+            out[key] = None
+            continue
+        assert t.shape[0] == sizes[rank], (key, t.shape, sizes[rank])
+        if len(set(sizes)) == 1:
+            full = torch.empty((num_envs,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+            dist.all_gather_into_tensor(full, t.contiguous(), group=group)
+        else:
+            pad = max(sizes)
+            buf = torch.zeros((pad,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+            buf[: t.shape[0]] = t
+            parts = [torch.empty_like(buf) for _ in range(world)]
+            dist.all_gather(parts, buf, group=group)
+            full = torch.cat([p[:n] for p, n in zip(parts, sizes)], dim=0)
+        out[key] = full
+    return out
+
+
+class ShardedKSVecEnv:
+    """``num_envs`` environments spread over the ranks of a ``torch.distributed`` group.
+
+    ``step_device(actions)`` takes the FULL action batch ``[num_envs, J]`` (every rank holds the
+    replicated policy output), steps the local shard, and all-gathers the results so that every
+    rank returns full-batch tensors.  Results equal the single-GPU run bit for bit because an
+    env's arithmetic does not depend on where it lives.
+
+    ``env_factory(local_num_envs)`` builds the local env (default: ``KSVecEnv``).
+    """
+
+    def __init__(self, num_envs: int, config: Optional[dict] = None, group=None,
+                 env_factory: Optional[Callable] = None, **kwargs):
+        self.group = group
+        self.world_size = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.num_envs = num_envs
+        self.lo, self.hi = shard_range(num_envs, self.rank, self.world_size)
+        if env_factory is None:
+            from .env import KSVecEnv
+
+            env_factory = lambda n: KSVecEnv(n, config, **kwargs)  # noqa: E731
+        self.local = env_factory(self.hi - self.lo)
+
+    @property
+    def local_num_envs(self) -> int:
+        return self.hi - self.lo
+
+    def local_slice(self, full: torch.Tensor) -> torch.Tensor:
+        """This rank's rows of a full-batch tensor (actions, initial conditions, ...)."""
+        return full[self.lo:self.hi]
+
+    def gather(self, local: dict) -> dict:
+        if self.world_size == 1:
+            return dict(local)
+        return gather_batch(local, self.num_envs, self.group)
+
+    def step_device(self, actions: torch.Tensor, gather: bool = True) -> dict:
+        out = self.local.step_device(self.local_slice(actions.reshape(self.num_envs, -1)))
+        return self.gather(out) if gather else out
+
+    def reset_device(self, seed: Optional[int] = None, **kwargs) -> None:
+        # distinct Philox streams per rank: env index inside the key is local, so offset the seed
+        s = None if seed is None else seed + 0x9E3779B97F4A7C15 * self.rank
+        self.local.reset_device(seed=s, **kwargs)
+
+    def set_state(self, u_full, timestep_full=None) -> None:
+        ts = None if timestep_full is None else timestep_full[self.lo:self.hi]
+        self.local.set_state(u_full[self.lo:self.hi], ts)
+
+    def close(self) -> None:
+        self.local.close()
