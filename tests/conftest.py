@@ -7,7 +7,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-GOLDEN = os.path.join(ROOT, "tests", "golden")
+if os.path.dirname(os.path.abspath(__file__)) not in sys.path:
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 
 
 def pytest_configure(config):
@@ -26,17 +27,3 @@ def _built_library():
     from oracle import ks_c
 
     ks_c.build()
-
-
-def load_golden(name):
-    import numpy as np
-
-    return np.load(os.path.join(GOLDEN, name + ".npz"))
-
-
-STEP_CASES = [
-    "kat1_default_1period", "kat2_default_10periods", "kat3_large_1period", "attractor_default_random",
-    "attractor_default_zero_action", "attractor_default_saturated", "attractor_default_action1d",
-    "truncation_edge", "attractor_large_random", "attractor_n128_random", "short_period_cfg10",
-    "attractor_n96_random",
-]

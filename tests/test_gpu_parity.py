@@ -9,16 +9,12 @@ relative L2 in fp64 (<= 1e-4 in fp32 mode); rewards to the same level; flags / c
 import numpy as np
 import pytest
 
-from conftest import STEP_CASES, load_golden
+from ks_testutil import STEP_CASES, load_golden, rel_l2
 
 pytestmark = pytest.mark.gpu
 
 TOL64 = 1e-10   # north star: "<= 1e-10 relative L2 in fp64"
 TOL32 = 1e-4    # north star: "<= 1e-4 in an optional fp32 mode"
-
-
-def rel_l2(a, b):
-    return np.linalg.norm(a - b, axis=-1) / np.linalg.norm(b, axis=-1)
 
 
 def make_env(g, num_envs, **kw):
