@@ -65,7 +65,8 @@ typedef struct ks_config {
     int32_t reward_mode;       /* enum ks_reward_mode */
     int32_t device;            /* CUDA device ordinal */
     int32_t points_per_lane;   /* 0 = choose automatically; else P with N % P == 0, 4<=P<=16 */
-    int32_t reserved;
+    int32_t obs_stride;        /* SensorTransform stride s: obs = u[s/2::s] (transforms.py:236-239);
+                                  0 or 1 = full state (what the MBRL loop uses, mbrl.py:171,174) */
     double L;                  /* domain length (22.0) */
     double dt;                 /* RK4 step (1e-3) */
     const float *forcing;      /* host, [J*N] row-major float32: GaussianForcing.forcing
@@ -101,7 +102,8 @@ int ks_reset(ks_handle *h, const double *u0, const uint8_t *mask, int where, uin
 /* KuramotoSivashinskyEnv.step for all B envs (kuramoto.py:78-98), one launch, device buffers.
  *   actions  dev [B,J] float32 (np.array(action, float32), kuramoto.py:79)
  *   phi      dev [B,N] float32 or NULL; non-NULL overrides the in-kernel `a @ F` FMA chain
- *   obs      dev [B,N] float32: float32 cast of the new state (what gym's vector env hands on)
+ *   obs      dev [B,No] float32: float32 cast of the new state (what gym's vector env hands on),
+ *                               No = N, or ceil((N - s/2)/s) sensors when obs_stride = s > 1
  *   reward   dev [B]   float64: mean over sub-steps of the pre-step reward (kuramoto.py:84,96)
  *   truncated dev [B]  uint8:   timestep >= max_episode_steps (kuramoto.py:93)
  *   step     dev [B]   int32:   info["step"] (kuramoto.py:98)
@@ -119,7 +121,7 @@ int ks_rollout(ks_handle *h, int32_t K, const float *actions, float *obs, double
 /* Host-buffer form of ks_step -- the call the gym-facing wrapper makes when the policy lives on
  * the host (worker.py:60-66): copies actions host->device, runs the period, copies ONE packed
  * output block device->host and synchronises.  Layout of the block (see ks_out_layout):
- *   reward f64 [B] | obs f32 [B*N] | step i32 [B] | truncated u8 [B] | nonfinite u8 [B]
+ *   reward f64 [B] | obs f32 [B*No] | step i32 [B] | truncated u8 [B] | nonfinite u8 [B]
  * (each part 16-byte aligned). */
 int ks_step_host(ks_handle *h, const float *actions_host, void *out_host, void *stream);
 /* offsets[5] = byte offsets of {reward, obs, step, truncated, nonfinite}; *total = block bytes. */

@@ -37,7 +37,7 @@ class KsConfig(ctypes.Structure):
         ("reward_mode", ctypes.c_int32),
         ("device", ctypes.c_int32),
         ("points_per_lane", ctypes.c_int32),
-        ("reserved", ctypes.c_int32),
+        ("obs_stride", ctypes.c_int32),
         ("L", ctypes.c_double),
         ("dt", ctypes.c_double),
         ("forcing", ctypes.c_void_p),

@@ -40,7 +40,7 @@ struct DeviceGuard {
 
 struct ks_handle {
     ks_config cfg;
-    int P = 0, lanes = 0, envs_per_warp = 0, grid = 0, regs = 0;
+    int P = 0, lanes = 0, envs_per_warp = 0, grid = 0, regs = 0, obs_len = 0;
     const void *kernel = nullptr;
     ks::Coef<double> c64;
     ks::Coef<float> c32;
@@ -253,6 +253,8 @@ int launch_period(ks_handle *h, int K, const float *actions, const float *phi, f
     p.lanes = h->lanes;
     p.envs_per_warp = h->envs_per_warp;
     p.reset_timestep = reset_timestep;
+    p.obs_stride = h->cfg.obs_stride < 1 ? 1 : h->cfg.obs_stride;
+    p.obs_len = h->obs_len;
     p.inv_cfg_steps = 1.0 / h->cfg.cfg_steps;
     p.inv_N = 1.0 / h->cfg.N;
     void *args[2] = {&p, h->cfg.precision == KS_F64 ? (void *)&h->c64 : (void *)&h->c32};
@@ -283,6 +285,7 @@ int ks_create(const ks_config *cfg, ks_handle **out)
         return fail(nullptr, KS_ERR_ARG, "ks_create: config out of range (num_envs=%d N=%d J=%d cfg_steps=%d L=%g dt=%g)",
                     cfg->num_envs, cfg->N, cfg->J, cfg->cfg_steps, cfg->L, cfg->dt);
     if (cfg->precision != KS_F64 && cfg->precision != KS_F32) return fail(nullptr, KS_ERR_ARG, "ks_create: bad precision");
+    if (cfg->obs_stride < 0 || cfg->obs_stride > cfg->N) return fail(nullptr, KS_ERR_ARG, "ks_create: bad obs_stride");
     if (cfg->reward_mode != KS_REWARD_L2 && cfg->reward_mode != KS_REWARD_DISSIPATION)
         return fail(nullptr, KS_ERR_ARG, "ks_create: bad reward_mode");
 
@@ -312,6 +315,9 @@ int ks_create(const ks_config *cfg, ks_handle **out)
     h->cfg.forcing = nullptr;
     h->cfg.points_per_lane = P;
     h->P = P;
+    const int stride = cfg->obs_stride < 1 ? 1 : cfg->obs_stride;
+    h->cfg.obs_stride = stride;
+    h->obs_len = (cfg->N - stride / 2 + stride - 1) / stride;
     h->lanes = cfg->N / P;
     h->envs_per_warp = 32 / h->lanes;
     const long long warps = ((long long)cfg->num_envs + h->envs_per_warp - 1) / h->envs_per_warp;
@@ -328,7 +334,7 @@ int ks_create(const ks_config *cfg, ks_handle **out)
     const size_t esz = f64 ? sizeof(double) : sizeof(float);
     h->out_off[0] = 0;
     h->out_off[1] = align16(B * sizeof(double));
-    h->out_off[2] = h->out_off[1] + align16(B * N * sizeof(float));
+    h->out_off[2] = h->out_off[1] + align16(B * (size_t)h->obs_len * sizeof(float));
     h->out_off[3] = h->out_off[2] + align16(B * sizeof(int32_t));
     h->out_off[4] = h->out_off[3] + align16(B);
     h->out_total = h->out_off[4] + align16(B);

@@ -54,6 +54,8 @@ struct Params {
     int lanes;             // lanes per environment (N = lanes * P)
     int envs_per_warp;     // 32 / lanes
     int reset_timestep;    // 1: timestep = 0 after the launch (burn-in of reset())
+    int obs_stride;        // SensorTransform stride s: obs = u[s/2::s] (transforms.py:236-239); 1 = all
+    int obs_len;           // observation length, ceil((N - s/2) / s)
     double inv_cfg_steps, inv_N;
 };
 
@@ -138,15 +140,16 @@ __device__ __forceinline__ double select_signed(bool neg, int fwd_lo, int fwd_hi
     return __hiloint2double(neg ? fwd_hi : nbwd_hi, neg ? fwd_lo : bwd_lo);
 }
 
-// u < 0 exactly as IEEE compares it (so -0.0 is NOT negative, as in the reference's `u < 0`),
-// evaluated on the integer pipe: for non-NaN x,  x < 0  <=>  bits(x) > bits(-0.0) as unsigned.
-// -DKS_UPWIND_DSETP switches back to the FP64-pipe compare.
+// Upwind switch `u < 0` (kuramoto.py:122) on the integer pipe: the sign bit of the high word.
+// This equals the IEEE compare for every value except -0.0, and -0.0 cannot occur here: the state
+// is canonicalised (u + 0.0) when it is loaded and every later value is the result of an FMA whose
+// addend is not -0.0.  -DKS_UPWIND_DSETP switches to the FP64-pipe compare for cross-checking.
 __device__ __forceinline__ bool is_negative(double x)
 {
 #ifdef KS_UPWIND_DSETP
     return x < 0.0;
 #else
-    return (unsigned long long)__double_as_longlong(x) > 0x8000000000000000ULL;
+    return __double2hiint(x) < 0;
 #endif
 }
 __device__ __forceinline__ bool is_negative(float x) { return x < 0.0f; }
@@ -210,13 +213,38 @@ __device__ __forceinline__ void rk4_stage(T (&u)[P], T (&us)[P], T (&acc)[P], co
         for (int i = 0; i < P + 2 * H; ++i) nq[i] = -q[i];
     }
 
+    // merged linear part  -uxxxx - uxx + phi
+    T linv[P];
+#ifdef KS_LIN_SCATTER
+    // scatter order: every input h[j] is applied to all the outputs it touches back to back, so
+    // that consecutive DFMAs share one source operand (operand-reuse cache) -- the register file
+    // delivers only ~2 32-bit operands per lane per cycle, which FP64 ops with two register
+    // operands already use up (tools/microbench/issue_mix.cu)
+#pragma unroll
+    for (int i = 0; i < P; ++i) linv[i] = phi[i];
+#pragma unroll
+    for (int j = 0; j < P + 2 * H; ++j) {
+#pragma unroll
+        for (int i = 0; i < P; ++i) {
+            const int d = (i + H) - j;
+            if (d >= -4 && d <= 4) linv[i] = fma_t<T>(h[j], c.W[d < 0 ? -d : d], linv[i]);
+        }
+    }
+#else
 #pragma unroll
     for (int i = 0; i < P; ++i) {
         const int m = i + H;
-        // merged linear part  -uxxxx - uxx + phi
         T lin = fma_t<T>(c.W[0], h[m], phi[i]);
 #pragma unroll
         for (int k = 1; k <= 4; ++k) lin = fma_t<T>(c.W[k], h[m + k] + h[m - k], lin);
+        linv[i] = lin;
+    }
+#endif
+
+#pragma unroll
+    for (int i = 0; i < P; ++i) {
+        const int m = i + H;
+        const T lin = linv[i];
         // upwind part  -1/2 d/dx(u^2): sum_k A[k] * (neg ? q[m+k] : -q[m-k])
         // (in the dissipation-reward stage the upwind sum is needed on its own; otherwise the
         // chain simply continues from `lin`)
@@ -288,7 +316,7 @@ __global__ void __launch_bounds__(kBlockThreads) ks_period_kernel(const Params p
     T *ug = static_cast<T *>(p.u) + off;
     load_row<P>(ug, u);
 #pragma unroll
-    for (int i = 0; i < P; ++i) { us[i] = T(0); acc[i] = T(0); }
+    for (int i = 0; i < P; ++i) { u[i] += T(0); us[i] = T(0); acc[i] = T(0); }   // -0.0 -> +0.0
     int ts = p.timestep[env];
     bool was_bad = p.nonfinite[env] != 0;
 
@@ -345,10 +373,20 @@ __global__ void __launch_bounds__(kBlockThreads) ks_period_kernel(const Params p
         if (active) {
             const size_t kb = (size_t)k * p.B + env;
             if (p.obs != nullptr) {
-                float o[P];
+                if (p.obs_stride <= 1) {
+                    float o[P];
 #pragma unroll
-                for (int i = 0; i < P; ++i) o[i] = (float)u[i];
-                store_row<P>(p.obs + (size_t)k * p.B * p.N + off, o);
+                    for (int i = 0; i < P; ++i) o[i] = (float)u[i];
+                    store_row<P>(p.obs + (size_t)k * p.B * p.N + off, o);
+                } else {
+                    float *orow = p.obs + ((size_t)k * p.B + env) * p.obs_len;
+                    const int first = p.obs_stride / 2;
+#pragma unroll
+                    for (int i = 0; i < P; ++i) {
+                        const int idx = l * P + i - first;
+                        if (idx >= 0 && idx % p.obs_stride == 0) orow[idx / p.obs_stride] = (float)u[i];
+                    }
+                }
             }
             if (l == 0) {
                 if (p.reward != nullptr) p.reward[kb] = -(tot * p.inv_N) * p.inv_cfg_steps;

@@ -56,6 +56,10 @@ class KSVecEnv(VectorEnvBase):
                       auto-resets always use the device generator with a fresh OS seed (the
                       reference reseeds from OS entropy there, kuramoto.py:101).
     ``burnin_periods`` override of ``int(200/dt/cfg_steps)`` (= 800) no-op periods in ``reset``
+    ``sensor_stride`` observation sampling fused into the kernel's output stage: observations are
+                      ``u[..., stride//2::stride]`` as ``SensorTransform(stride)`` would return
+                      (``pdegym/common/transforms.py:231-247``); 1 = full state, which is what the
+                      MBRL loop uses (``mbrl.py:171,174``).  The state itself is always full.
     """
 
     metadata = {"render.modes": ["rgb_array"]}
@@ -65,7 +69,7 @@ class KSVecEnv(VectorEnvBase):
     def __init__(self, num_envs: int, config: Optional[dict] = None, *, Xi: Optional[Sequence[float]] = None,
                  device: Optional[int] = None, precision: str = "f64", reward_mode: Optional[str] = None,
                  ic: str = "numpy", burnin_periods: Optional[int] = None, points_per_lane: int = 0,
-                 copy: bool = True, **kwargs):
+                 sensor_stride: int = 1, copy: bool = True, **kwargs):
         cfg = dict(config or {})
         cfg.update(kwargs)
         self.L = float(cfg.pop("L", 22.0))
@@ -90,6 +94,10 @@ class KSVecEnv(VectorEnvBase):
         if ic not in ("numpy", "device"):
             raise ValueError("ic must be 'numpy' or 'device'")
         self.reward_mode, self.precision, self.ic, self.copy = reward_mode, precision, ic, copy
+        self.sensor_stride = int(sensor_stride)
+        if not (1 <= self.sensor_stride <= self.N):
+            raise ValueError("sensor_stride must be in [1, N]")
+        self.obs_len = len(range(self.sensor_stride // 2, self.N, self.sensor_stride))
 
         self.dx = self.L / self.N                                                         # :55
         self.x = np.linspace(0.0, self.L - self.L / self.N, self.N, dtype=np.float32)     # :56
@@ -101,7 +109,7 @@ class KSVecEnv(VectorEnvBase):
         self.noop = np.zeros((1, self.J), dtype=np.float32)                               # :62
 
         single_action = Box(-1.0, 1.0, shape=(1, self.J), dtype=np.float32)               # :75
-        single_obs = Box(-np.inf, np.inf, shape=(1, self.N), dtype=np.float32)            # :76
+        single_obs = Box(-np.inf, np.inf, shape=(1, self.obs_len), dtype=np.float32)      # :76
         super().__init__(num_envs, single_obs, single_action)
 
         # ---- the CUDA side: fails loudly without the built library / a B200 ----
@@ -117,7 +125,7 @@ class KSVecEnv(VectorEnvBase):
             abi_version=_lib.KS_ABI_VERSION, num_envs=num_envs, N=self.N, J=self.J, cfg_steps=self.cfg_steps,
             max_episode_steps=self.max_episode_steps, burnin_periods=self.burnin_periods,
             precision=_lib.PRECISIONS[precision], reward_mode=_lib.REWARD_MODES[reward_mode],
-            device=self.device_index, points_per_lane=points_per_lane, reserved=0, L=self.L, dt=self.dt,
+            device=self.device_index, points_per_lane=points_per_lane, obs_stride=self.sensor_stride, L=self.L, dt=self.dt,
             forcing=self._F_host.ctypes.data)
         handle = ctypes.c_void_p()
         torch.cuda.init()
@@ -131,7 +139,7 @@ class KSVecEnv(VectorEnvBase):
         self._out_pinned = torch.empty(total.value, dtype=torch.uint8, pin_memory=True)
         host = self._out_pinned.numpy()
         self._h_reward = host[offs[0]:offs[0] + 8 * B].view(np.float64)
-        self._h_obs = host[offs[1]:offs[1] + 4 * B * N].view(np.float32).reshape(B, 1, N)
+        self._h_obs = host[offs[1]:offs[1] + 4 * B * self.obs_len].view(np.float32).reshape(B, 1, self.obs_len)
         self._h_step = host[offs[2]:offs[2] + 4 * B].view(np.int32)
         self._h_trunc = host[offs[3]:offs[3] + B].view(np.uint8)
         self._h_bad = host[offs[4]:offs[4] + B].view(np.uint8)
@@ -257,7 +265,7 @@ class KSVecEnv(VectorEnvBase):
         self._reset_impl(seed, u0, None, burnin_periods)
         u, ts = self.get_state()
         self._raise_if_nonfinite(u)
-        obs = u.astype(np.float32).reshape(self.num_envs, 1, self.N)
+        obs = self._observe(u)
         if return_info:
             return obs, {"step": ts.astype(np.int64), "_step": np.ones(self.num_envs, dtype=bool)}
         return obs
@@ -298,18 +306,22 @@ class KSVecEnv(VectorEnvBase):
             u, _ = self.get_state()
             finals = np.empty(self.num_envs, dtype=object)
             for i in np.nonzero(truncated)[0]:
-                finals[i] = u[i].reshape(1, self.N)
+                finals[i] = u[i, self.sensor_stride // 2::self.sensor_stride].reshape(1, self.obs_len)
             infos["final_observation"] = finals
             infos["_final_observation"] = truncated.copy()
             self._reset_impl(None, None, None if truncated.all() else truncated, None)
             u_new, _ = self.get_state()
             obs = np.array(obs)
-            obs[truncated] = u_new[truncated].astype(np.float32).reshape(-1, 1, self.N)
+            obs[truncated] = self._observe(u_new[truncated])
         return obs, rewards, terminated, truncated, infos
 
     def step(self, actions):
         self.step_async(actions)
         return self.step_wait()
+
+    def _observe(self, u: np.ndarray) -> np.ndarray:
+        """float32 observation ``(B,1,No)`` of states ``u [B,N]`` (cast + sensor sampling)."""
+        return u[:, self.sensor_stride // 2::self.sensor_stride].astype(np.float32).reshape(-1, 1, self.obs_len)
 
     def _raise_if_nonfinite(self, u):
         if not np.all(np.isfinite(u)):
@@ -322,7 +334,7 @@ class KSVecEnv(VectorEnvBase):
             B, N, dev = self.num_envs, self.N, self.device
             lead = (B,) if K == 0 else (K, B)
             self._d_out = (key, dict(
-                obs=torch.empty(lead + (N,), dtype=torch.float32, device=dev),
+                obs=torch.empty(lead + (self.obs_len,), dtype=torch.float32, device=dev),
                 reward=torch.empty(lead, dtype=torch.float64, device=dev),
                 truncated=torch.empty(lead, dtype=torch.uint8, device=dev),
                 step=torch.empty(lead, dtype=torch.int32, device=dev),
@@ -334,7 +346,7 @@ class KSVecEnv(VectorEnvBase):
         stream, no host synchronisation, no auto-reset.  ``actions``: CUDA float32 ``[B,J]`` (or
         ``[B,1,J]``).  ``phi`` (CUDA float32 ``[B,N]``) overrides the in-kernel ``a @ F``.
         Returns a dict of CUDA tensors that are REUSED by the next call:
-        ``obs [B,N] f32, reward [B] f64, truncated [B] u8, step [B] i32, nonfinite [B] u8``."""
+        ``obs [B,No] f32, reward [B] f64, truncated [B] u8, step [B] i32, nonfinite [B] u8``."""
         self._check_open()
         out = self._device_outputs(0)
         a = None

@@ -13,6 +13,7 @@ if os.path.dirname(os.path.abspath(__file__)) not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (B200); run with -m gpu on the GPU box")
+    config.addinivalue_line("markers", "slow: a few seconds of CPU work")
 
 
 @pytest.fixture(scope="session", autouse=True)

@@ -173,7 +173,8 @@ def test_rollout_equals_repeated_steps_bitwise():
     from model_based_pde_control_b200 import KSVecEnv
 
     B, K = 21, 4
-    env = KSVecEnv(B, dict(cfg_steps=25))
+    env = KSVecEnv(B, dict(cfg_steps=25, Tmax=10.0))     # 10 / (1e-3 * 25) = 400 steps per episode
+    assert env.max_episode_steps == 400
     rng = np.random.default_rng(11)
     u0 = rng.uniform(-1.5, 1.5, (B, 64))
     acts = torch.as_tensor(rng.uniform(-1, 1, (K, B, 4)).astype(np.float32)).cuda()

@@ -1,0 +1,87 @@
+"""Host-side mirror of the reference interface: forcing transform, spaces, factories, sharding
+arithmetic, and the loud failure without CUDA.  CPU only."""
+import numpy as np
+import pytest
+import torch
+
+import model_based_pde_control_b200 as pkg
+from ks_testutil import load_golden
+from model_based_pde_control_b200.forcing import GaussianForcing
+from model_based_pde_control_b200.sharding import shard_range
+from model_based_pde_control_b200.spaces import Box, batch_space
+
+
+@pytest.mark.parametrize("name", ["kat1_default_1period", "kat3_large_1period", "attractor_n128_random",
+                                  "attractor_n96_random"])
+def test_forcing_matrix_bit_identical_to_reference(name):
+    g = load_golden(name)
+    f = GaussianForcing(g["x"], g["Xi"], float(g["sigma"]), float(g["L"]), int(g["N"]))
+    assert f.matrix().dtype == np.float32 and np.array_equal(f.matrix(), g["F"])
+    assert f.J == len(g["Xi"])
+
+
+def test_forcing_call_and_inverse():
+    g = load_golden("forcing_kat")
+    x = np.linspace(0.0, 22.0 - 22.0 / 64, 64, dtype=np.float32)
+    f = GaussianForcing(x, [0, .25, .5, .75], 0.4, 22.0, 64)
+    phi = f(g["A"][:1])                       # numpy in -> numpy out, as Transform.convert/unconvert
+    assert isinstance(phi, np.ndarray) and phi.dtype == np.float32 and np.array_equal(phi[0], g["phi"][0])
+    t = f(torch.from_numpy(g["A"][:4]))
+    assert isinstance(t, torch.Tensor) and np.array_equal(t.numpy(), g["phi"][:4])
+    # Inverse samples the pattern at the jet positions and undoes the 4x4 mixing (transforms.py:267-279)
+    back = f.Inverse(phi)
+    assert np.allclose(back, g["A"][:1], atol=2e-5)
+    assert f.Inverse.Inverse is f
+    assert f.Inverse.xpos.tolist() == [0, 16, 32, 48]
+
+
+def test_spaces_and_batching():
+    b = Box(-1.0, 1.0, shape=(1, 4), dtype=np.float32)
+    assert b.shape == (1, 4) and b.low.dtype == np.float32 and (b.high == 1).all()
+    s = b.sample()
+    assert s.shape == (1, 4) and s.dtype == np.float32 and b.contains(s)
+    bb = batch_space(b, 10)
+    assert bb.shape == (10, 1, 4) and bb.sample().shape == (10, 1, 4)
+    o = Box(-np.inf, np.inf, shape=(1, 64), dtype=np.float32)
+    assert np.isneginf(o.low).all() and o.sample().shape == (1, 64)
+
+
+def test_shard_ranges_cover_and_are_contiguous():
+    for n, w in [(4096, 1), (4096, 2), (65536, 8), (10, 4), (7, 8), (4097, 8)]:
+        ranges = [shard_range(n, r, w) for r in range(w)]
+        assert ranges[0][0] == 0 and ranges[-1][1] == n
+        assert all(a[1] == b[0] for a, b in zip(ranges, ranges[1:]))
+        sizes = [hi - lo for lo, hi in ranges]
+        assert max(sizes) - min(sizes) <= 1
+    assert shard_range(65536, 3, 8) == (24576, 32768)
+    with pytest.raises(ValueError):
+        shard_range(8, 8, 8)
+
+
+def test_package_surface_and_factories_fail_loudly_without_cuda():
+    assert pkg.ENV_ID == "KuramotoSivashinskyEnv-v0"
+    with pytest.raises(ValueError):
+        pkg.vector_make("SomethingElse-v0", num_envs=2)
+    with pytest.raises(ValueError):
+        pkg.make({}, new_step_api=False)
+    with pytest.raises(TypeError):
+        pkg.KSVecEnv(2, {"not_a_kwarg": 1})
+    with pytest.raises(ValueError):
+        pkg.KSVecEnv(2, precision="bf16")
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            pkg.make({}, num_envs=4)
+
+
+def test_product_package_never_imports_the_oracle():
+    """The oracle is test infrastructure; the product path must not route through it."""
+    import os
+    import re
+
+    root = os.path.dirname(os.path.abspath(pkg.__file__))
+    for dirpath, _, files in os.walk(root):
+        for fn in files:
+            if fn.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, fn)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), fn
+                assert "ks_oracle" not in text and "scipy" not in text, fn

@@ -1,0 +1,86 @@
+"""world_size-2 (and 3, ragged) gloo tests of the env sharding + all-gather layout on CPU.
+
+The local env is a deterministic stub (the CUDA env needs a GPU); what is tested is exactly what
+runs at N>1 on the GPU box around the kernel: which rows each rank steps and that the gathered
+full-batch tensors come back in env order on every rank."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from model_based_pde_control_b200.sharding import ShardedKSVecEnv, shard_range
+
+
+class StubEnv:
+    """step_device: obs[b] = 1000*global_id... derived only from the action rows it was given."""
+
+    def __init__(self, n, N=8):
+        self.num_envs, self.N = n, N
+        self.calls = 0
+
+    def step_device(self, actions):
+        assert actions.shape[0] == self.num_envs
+        self.calls += 1
+        key = actions[:, 0].double()
+        return {"obs": (key[:, None] * 10 + torch.arange(self.N)[None]).float(),
+                "reward": -key, "truncated": (key.long() % 2).to(torch.uint8), "nothing": None}
+
+    def set_state(self, u, ts=None):
+        self.u = u
+
+    def close(self):
+        pass
+
+
+def _worker(rank, world, port, num_envs, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        env = ShardedKSVecEnv(num_envs, env_factory=lambda n: StubEnv(n))
+        lo, hi = shard_range(num_envs, rank, world)
+        assert (env.lo, env.hi, env.local_num_envs) == (lo, hi, hi - lo)
+        actions = torch.arange(num_envs, dtype=torch.float32)[:, None].repeat(1, 4)   # row b carries id b
+        out = env.step_device(actions)
+        ids = torch.arange(num_envs, dtype=torch.float64)
+        ok = (torch.equal(out["reward"], -ids)
+              and torch.equal(out["obs"], (ids[:, None] * 10 + torch.arange(8)[None]).float())
+              and torch.equal(out["truncated"], (ids.long() % 2).to(torch.uint8))
+              and out["nothing"] is None and env.local.calls == 1)
+        local = env.step_device(actions, gather=False)
+        ok = ok and local["reward"].shape[0] == hi - lo and torch.equal(local["reward"], -ids[lo:hi])
+        env.set_state(torch.arange(num_envs * 8.0).reshape(num_envs, 8))
+        ok = ok and torch.equal(env.local.u, torch.arange(num_envs * 8.0).reshape(num_envs, 8)[lo:hi])
+        q.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+@pytest.mark.parametrize("world,num_envs", [(2, 16), (2, 4096), (3, 10)])
+def test_sharded_step_and_gather(world, num_envs):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, num_envs, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    results = dict(q.get(timeout=5) for _ in range(world))
+    assert results == {r: True for r in range(world)}
+
+
+def test_single_process_passthrough():
+    env = ShardedKSVecEnv(6, env_factory=lambda n: StubEnv(n))
+    assert (env.rank, env.world_size, env.lo, env.hi) == (0, 1, 0, 6)
+    out = env.step_device(torch.arange(6.0)[:, None].repeat(1, 4))
+    assert out["reward"].tolist() == [-0.0, -1.0, -2.0, -3.0, -4.0, -5.0]
