@@ -97,20 +97,29 @@ void fill_coef(ks::Coef<T> &c, double dx, double dt)
     c.dt_sixth = (T)(dt / 6.0);
 }
 
-// Points per lane for a grid of N points: lanes = N / P must fit one warp.  Preference: the
-// best lane utilisation (envs_per_warp * lanes / 32), then P = 8 (measured sweet spot between
-// halo overhead and registers), then the larger P.
-int choose_points_per_lane(int N)
+// Points per lane P for a grid of N points and a batch of B envs (lanes = N / P must fit one warp).
+// Static cost model fitted to B200 measurements (profiles/round1_sweep.md): a warp costs about
+// c(P) = 196 P + 135 cycles per RK4 sub-step when the SM sub-partition (SMSP) is saturated
+// (register-file operand bandwidth bound), an SMSP with few warps is latency-bound at about 3500
+// cycles per sub-step, and the launch takes as long as the fullest SMSP:
+//     T(P) = max(3500, ceil(warps(P) / #SMSP) * c(P)),  warps(P) = ceil(B / (32 / lanes)).
+// Smallest T wins; ties go to the larger P (less halo overhead).  The choice is deterministic in
+// (N, B, #SM) so that every rank of a sharded run picks the same layout.
+int choose_points_per_lane(int N, long long B, int sm_count)
 {
     int best = 0;
-    double best_score = -1.0;
+    double best_t = 0.0;
+    const long long smsp = 4LL * (sm_count > 0 ? sm_count : 148);
     for (int P = ks::kMinP; P <= ks::kMaxP; ++P) {
         if (N % P) continue;
         const int lanes = N / P;
         if (lanes < 1 || lanes > 32) continue;
-        const double util = double((32 / lanes) * lanes) / 32.0;
-        const double score = util * 100.0 + (P == 8 ? 2.0 : 0.0) + P * 0.01;
-        if (score > best_score) { best_score = score; best = P; }
+        const long long epw = 32 / lanes;
+        const long long warps = (B + epw - 1) / epw;
+        const long long per_smsp = (warps + smsp - 1) / smsp;
+        double t = (double)per_smsp * (196.0 * P + 135.0);
+        if (t < 3500.0) t = 3500.0;
+        if (best == 0 || t <= best_t) { best_t = t; best = P; }
     }
     return best;
 }
@@ -290,11 +299,13 @@ int ks_create(const ks_config *cfg, ks_handle **out)
         return fail(nullptr, KS_ERR_ARG, "ks_create: bad reward_mode");
 
     int P = cfg->points_per_lane;
-    if (P == 0) P = choose_points_per_lane(cfg->N);
-    if (P < ks::kMinP || P > ks::kMaxP || cfg->N % P || cfg->N / P > 32)
+    if (P != 0 && (P < ks::kMinP || P > ks::kMaxP || cfg->N % P || cfg->N / P > 32))
         return fail(nullptr, KS_ERR_UNSUPPORTED,
                     "ks_create: N=%d needs N = lanes*P with 4<=P<=16, lanes<=32 (points_per_lane=%d)", cfg->N,
                     cfg->points_per_lane);
+    if (P == 0 && choose_points_per_lane(cfg->N, cfg->num_envs, 0) == 0)
+        return fail(nullptr, KS_ERR_UNSUPPORTED, "ks_create: N=%d cannot be split as lanes*P with 4<=P<=16, lanes<=32",
+                    cfg->N);
 
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -308,6 +319,7 @@ int ks_create(const ks_config *cfg, ks_handle **out)
     if (cudaGetDeviceProperties(&prop, cfg->device) != cudaSuccess || prop.major != 10)
         return fail(nullptr, KS_ERR_NO_DEVICE, "ks_create: device %d is sm_%d%d; kernels are built for sm_100a only",
                     cfg->device, prop.major, prop.minor);
+    if (P == 0) P = choose_points_per_lane(cfg->N, cfg->num_envs, prop.multiProcessorCount);
 
     ks_handle *h = new (std::nothrow) ks_handle();
     if (!h) return fail(nullptr, KS_ERR_ARG, "ks_create: out of host memory");
