@@ -139,7 +139,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "100",
+                ["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "20",
                  "-i", str(self.gpu_index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.proc = None
@@ -181,7 +181,7 @@ def run_gpu_arm(args):
     import torch.distributed as dist
 
     from model_based_pde_control_b200 import KSVecEnv, _lib
-    from model_based_pde_control_b200.sharding import gather_batch
+    from model_based_pde_control_b200.sharding import gather_packed
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -210,10 +210,12 @@ def run_gpu_arm(args):
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
     stream = torch.cuda.current_stream(dev)
 
+    fields = env.packed_fields()
+
     def one_step(k):
         out = env.step_device(actions[k])
         if world > 1:
-            out = gather_batch({"obs": out["obs"], "reward": out["reward"], "truncated": out["truncated"]}, total_envs)
+            out = gather_packed(out["packed"], fields, B)
         return out
 
     for k in range(W):
@@ -306,7 +308,7 @@ def run_gpu_arm(args):
                         "random actions (BASELINE.json configs[1] per GPU)",
             "envs_per_gpu": B, "total_envs": total_envs, "N": N, "J": J, "cfg_steps": S,
             "l2": "flushed (256 MiB memset) between timed steps, outside the per-step event pairs",
-            "collective": "none (N=1)" if world == 1 else "NCCL all-gather of obs/reward/truncated per period, timed",
+            "collective": "none (N=1)" if world == 1 else "one NCCL all-gather of the packed obs/reward/step/truncated/flags block per period, timed",
             "layout": env.launch_info(),
         },
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": env.h2d_bytes_per_step,

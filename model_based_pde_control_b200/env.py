@@ -136,6 +136,7 @@ class KSVecEnv(VectorEnvBase):
         total = ctypes.c_size_t()
         _lib.check(self._h, lib.ks_out_layout(self._h, ctypes.byref(offs), ctypes.byref(total)))
         B, N = num_envs, self.N
+        self._out_offsets = [int(x) for x in offs]
         self._out_pinned = torch.empty(total.value, dtype=torch.uint8, pin_memory=True)
         host = self._out_pinned.numpy()
         self._h_reward = host[offs[0]:offs[0] + 8 * B].view(np.float64)
@@ -329,24 +330,48 @@ class KSVecEnv(VectorEnvBase):
 
     # ------------------------------------------------------------------ device-tensor API
     def _device_outputs(self, K: int):
+        """Output tensors of the device API.  For a single period (K = 0) all five are typed views
+        into ONE contiguous byte block with the layout of ``ks_out_layout`` -- a sharded run
+        all-gathers that block with a single collective (``sharding.gather_packed``)."""
         key = K
         if self._d_out is None or self._d_out[0] != key:
-            B, N, dev = self.num_envs, self.N, self.device
-            lead = (B,) if K == 0 else (K, B)
-            self._d_out = (key, dict(
-                obs=torch.empty(lead + (self.obs_len,), dtype=torch.float32, device=dev),
-                reward=torch.empty(lead, dtype=torch.float64, device=dev),
-                truncated=torch.empty(lead, dtype=torch.uint8, device=dev),
-                step=torch.empty(lead, dtype=torch.int32, device=dev),
-                nonfinite=torch.empty(lead, dtype=torch.uint8, device=dev)))
+            B, dev = self.num_envs, self.device
+            if K == 0:
+                offs, total = self._out_offsets, self.d2h_bytes_per_step
+                block = torch.zeros(total, dtype=torch.uint8, device=dev)
+
+                def view(i, nbytes, dtype, shape):
+                    return block[offs[i]:offs[i] + nbytes].view(dtype).reshape(shape)
+
+                out = dict(reward=view(0, 8 * B, torch.float64, (B,)),
+                           obs=view(1, 4 * B * self.obs_len, torch.float32, (B, self.obs_len)),
+                           step=view(2, 4 * B, torch.int32, (B,)),
+                           truncated=view(3, B, torch.uint8, (B,)),
+                           nonfinite=view(4, B, torch.uint8, (B,)), packed=block)
+            else:
+                lead = (K, B)
+                out = dict(obs=torch.empty(lead + (self.obs_len,), dtype=torch.float32, device=dev),
+                           reward=torch.empty(lead, dtype=torch.float64, device=dev),
+                           truncated=torch.empty(lead, dtype=torch.uint8, device=dev),
+                           step=torch.empty(lead, dtype=torch.int32, device=dev),
+                           nonfinite=torch.empty(lead, dtype=torch.uint8, device=dev))
+            self._d_out = (key, out)
         return self._d_out[1]
+
+    def packed_fields(self) -> dict:
+        """``{name: (byte offset, torch dtype, per-env shape)}`` of the packed single-period block."""
+        o = self._out_offsets
+        return {"reward": (o[0], torch.float64, ()), "obs": (o[1], torch.float32, (self.obs_len,)),
+                "step": (o[2], torch.int32, ()), "truncated": (o[3], torch.uint8, ()),
+                "nonfinite": (o[4], torch.uint8, ())}
 
     def step_device(self, actions: torch.Tensor, phi: Optional[torch.Tensor] = None) -> dict:
         """One control period with device-resident inputs and outputs; asynchronous on the current
         stream, no host synchronisation, no auto-reset.  ``actions``: CUDA float32 ``[B,J]`` (or
         ``[B,1,J]``).  ``phi`` (CUDA float32 ``[B,N]``) overrides the in-kernel ``a @ F``.
         Returns a dict of CUDA tensors that are REUSED by the next call:
-        ``obs [B,No] f32, reward [B] f64, truncated [B] u8, step [B] i32, nonfinite [B] u8``."""
+        ``obs [B,No] f32, reward [B] f64, truncated [B] u8, step [B] i32, nonfinite [B] u8`` (views
+        of one contiguous block, also returned as ``packed``)."""
         self._check_open()
         out = self._device_outputs(0)
         a = None

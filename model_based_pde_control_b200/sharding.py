@@ -53,6 +53,27 @@ def gather_batch(local: dict, num_envs: int, group=None) -> dict:
     return out
 
 
+def gather_packed(packed_local: torch.Tensor, fields: dict, local_envs: int, group=None) -> dict:
+    """ONE all-gather of every rank's packed output block (``KSVecEnv.step_device()["packed"]``,
+    layout of ``ks_out_layout``) -- obs, reward, step, truncated and flags travel in a single NCCL
+    collective.  Equal shards only.  Returns ``{name: tensor [world, local_envs, ...]}``: strided
+    views into the gathered buffer in rank (= env) order; ``.reshape(world * local_envs, ...)``
+    gives the flat batch (a copy)."""
+    world = dist.get_world_size(group)
+    total = packed_local.numel()
+    full = torch.empty(world * total, dtype=torch.uint8, device=packed_local.device)
+    dist.all_gather_into_tensor(full, packed_local, group=group)
+    rows = full.view(world, total)
+    out = {}
+    for name, (off, dtype, shape) in fields.items():
+        n = local_envs
+        for d in shape:
+            n *= d
+        nbytes = n * torch.empty((), dtype=dtype).element_size()
+        out[name] = rows[:, off:off + nbytes].view(dtype).reshape((world, local_envs) + tuple(shape))
+    return out
+
+
 class ShardedKSVecEnv:
     """``num_envs`` environments spread over the ranks of a ``torch.distributed`` group.
 
@@ -91,8 +112,16 @@ class ShardedKSVecEnv:
         return gather_batch(local, self.num_envs, self.group)
 
     def step_device(self, actions: torch.Tensor, gather: bool = True) -> dict:
+        """Step the local shard with this rank's rows of the full action batch.  ``gather=True``
+        returns full-batch tensors ``[num_envs, ...]``; ``gather="packed"`` uses the single-
+        collective path and returns ``[world, local_envs, ...]`` views (equal shards)."""
         out = self.local.step_device(self.local_slice(actions.reshape(self.num_envs, -1)))
-        return self.gather(out) if gather else out
+        if not gather:
+            return out
+        if gather == "packed" and self.world_size > 1:
+            return gather_packed(out["packed"], self.local.packed_fields(), self.local_num_envs, self.group)
+        out = {k: v for k, v in out.items() if k != "packed"}
+        return self.gather(out)
 
     def reset_device(self, seed: Optional[int] = None, **kwargs) -> None:
         # distinct Philox streams per rank: env index inside the key is local, so offset the seed

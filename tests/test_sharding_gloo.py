@@ -51,6 +51,21 @@ def _worker(rank, world, port, num_envs, q):
               and out["nothing"] is None and env.local.calls == 1)
         local = env.step_device(actions, gather=False)
         ok = ok and local["reward"].shape[0] == hi - lo and torch.equal(local["reward"], -ids[lo:hi])
+        if num_envs % world == 0:
+            # single-collective path: per-rank packed block [reward f64 | obs f32 | flag u8], 16-byte aligned parts
+            n = hi - lo
+            off_obs = (8 * n + 15) // 16 * 16
+            off_flag = off_obs + (4 * n * 8 + 15) // 16 * 16
+            block = torch.zeros(off_flag + (n + 15) // 16 * 16, dtype=torch.uint8)
+            block[:8 * n].view(torch.float64).copy_(local["reward"])
+            block[off_obs:off_obs + 4 * n * 8].view(torch.float32).copy_(local["obs"].reshape(-1))
+            block[off_flag:off_flag + n].copy_(local["truncated"])
+            from model_based_pde_control_b200.sharding import gather_packed
+            g = gather_packed(block, {"reward": (0, torch.float64, ()), "obs": (off_obs, torch.float32, (8,)),
+                                      "truncated": (off_flag, torch.uint8, ())}, n)
+            ok = ok and g["reward"].shape == (world, n) and torch.equal(g["reward"].reshape(-1), -ids)
+            ok = ok and torch.equal(g["obs"].reshape(num_envs, 8), out["obs"])
+            ok = ok and torch.equal(g["truncated"].reshape(-1), out["truncated"])
         env.set_state(torch.arange(num_envs * 8.0).reshape(num_envs, 8))
         ok = ok and torch.equal(env.local.u, torch.arange(num_envs * 8.0).reshape(num_envs, 8)[lo:hi])
         q.put((rank, bool(ok)))
