@@ -298,6 +298,15 @@ def run_gpu_arm(args):
     bytes_per_launch = (2 * esz * N + 4 * N + 4 * J + 16) * B     # 20N+4J+16 per env (fp64)
     hbm_achieved = bytes_per_launch / (kernel_ms * 1e-3) / 1e9
 
+    traffic, traffic_src = None, None
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            t = json.load(f).get(f"{args.precision}/envs{B}/P{env.launch_info()['points_per_lane']}")
+        if t:
+            traffic, traffic_src = t["dram_bytes_read"] + t["dram_bytes_write"], t["source"]
+    except Exception:
+        pass
+
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -318,7 +327,8 @@ def run_gpu_arm(args):
         "clocks": clocks,
         "roofline": {
             "bound": "fp64", "kernel": "ks_period_kernel", "achieved": achieved_tf, "peak": fp64_peak,
-            "unit": "TFLOP/s", "frac": achieved_tf / fp64_peak, "traffic": None,
+            "unit": "TFLOP/s", "frac": achieved_tf / fp64_peak, "traffic": traffic,
+            "traffic_unit": "bytes per launch (dram read+write, ncu --set full)", "traffic_source": traffic_src,
             "peak_source": peak_src, "peak_nominal": FP64_NOMINAL_TFLOPS, "frac_of_nominal": achieved_tf / FP64_NOMINAL_TFLOPS,
             "flops_per_launch": flops_per_launch, "flops_model": "191*N*cfg_steps per env-period (SURVEY.md 8d)",
             "kernel_ms": kernel_ms,
