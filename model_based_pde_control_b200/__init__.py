@@ -9,10 +9,12 @@ The package holds only what that path needs: ``csrc/`` (CUDA kernels + C ABI), t
 binding, the host mirror of the gym-facing interface, and the env-sharding helper for
 multi-GPU runs.  Importing it does not require a GPU; constructing an env does.
 """
+from .device_pipeline import DeviceEnvPipeline, RolloutBatch, ScaleTransformDevice, SensorTransformDevice
 from .env import KSVecEnv
 from .forcing import GaussianForcing
 from .registration import ENV_ID, make, vector_make
 from .sharding import ShardedKSVecEnv, shard_range
 
-__all__ = ["KSVecEnv", "GaussianForcing", "ENV_ID", "make", "vector_make", "ShardedKSVecEnv", "shard_range"]
+__all__ = ["KSVecEnv", "GaussianForcing", "ENV_ID", "make", "vector_make", "ShardedKSVecEnv", "shard_range",
+           "DeviceEnvPipeline", "RolloutBatch", "ScaleTransformDevice", "SensorTransformDevice"]
 __version__ = "0.1.0"

@@ -12,11 +12,13 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB_PATH = os.path.join(_HERE, "_build", "libks_oracle.so")
+_LIB_PATH = os.environ.get("KS_ORACLE_LIB") or os.path.join(_HERE, "_build", "libks_oracle.so")
 _lib = None
 
 
 def build(force: bool = False) -> str:
+    if os.environ.get("KS_ORACLE_LIB"):      # caller supplies its own build (e.g. -march=native)
+        return _LIB_PATH
     src = os.path.join(_HERE, "ks_oracle.c")
     if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < os.path.getmtime(src):
         subprocess.run(["make", "-C", _HERE, "-B" if force else "-s", "all"], check=True,

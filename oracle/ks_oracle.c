@@ -42,21 +42,37 @@ void kso_forcing(int B, int J, int N, const float *actions, const float *F, floa
         }
 }
 
-/* derivative triple of one env; w = work array of N doubles holding u*u */
+/* derivative triple of one env.  q = work array of N doubles (receives u*u).
+ * Periodic indexing goes through two halo-padded copies so that the stencil loops have fixed
+ * offsets (no modulo) and vectorise; the order of floating-point operations per output point is
+ * exactly the one of the straightforward loops (the compiler may not re-associate: no -ffast-math,
+ * -ffp-contract=off). */
 static void derivs(int N, double dx, const double *u, double *q, double *ux, double *uxx, double *uxxxx)
 {
     const double dx2 = dx * dx, dx4 = dx2 * dx2;
-    for (int i = 0; i < N; ++i) q[i] = u[i] * u[i];
+    double up[KSO_MAX_N + 8], qp[KSO_MAX_N + 8];
     for (int i = 0; i < N; ++i) {
-        double fwd = UPWIND[0] * q[i], bwd = -UPWIND[0] * q[i];
+        q[i] = u[i] * u[i];
+        up[i + 4] = u[i];
+        qp[i + 4] = q[i];
+    }
+    for (int k = 0; k < 4; ++k) {
+        up[k] = u[N - 4 + k];
+        qp[k] = q[N - 4 + k];
+        up[N + 4 + k] = u[k];
+        qp[N + 4 + k] = q[k];
+    }
+    for (int i = 0; i < N; ++i) {
+        const double *qc = qp + i + 4, *uc = up + i + 4;
+        double fwd = UPWIND[0] * qc[0], bwd = -UPWIND[0] * qc[0];
         for (int k = 1; k < 5; ++k) {
-            fwd = fwd + UPWIND[k] * q[(i + k) % N];
-            bwd = bwd - UPWIND[k] * q[(i - k + N) % N];
+            fwd = fwd + UPWIND[k] * qc[k];
+            bwd = bwd - UPWIND[k] * qc[-k];
         }
-        ux[i] = (u[i] < 0.0 ? fwd : bwd) / dx;
+        ux[i] = (uc[0] < 0.0 ? fwd : bwd) / dx;
         double s2 = 0.0, s4 = 0.0;
-        for (int k = -3; k <= 3; ++k) s2 = s2 + D2[k + 3] * u[(i + k + N) % N];
-        for (int k = -4; k <= 4; ++k) s4 = s4 + D4[k + 4] * u[(i + k + N) % N];
+        for (int k = -3; k <= 3; ++k) s2 = s2 + D2[k + 3] * uc[k];
+        for (int k = -4; k <= 4; ++k) s4 = s4 + D4[k + 4] * uc[k];
         uxx[i] = s2 / dx2;
         uxxxx[i] = s4 / dx4;
     }

@@ -83,6 +83,45 @@ class _Wrapper:
         return self.env.unwrapped
 
 
+class _VectorEnvWrapper:
+    """The behaviour of ``gym.vector.VectorEnvWrapper`` (0.25.2) the reference's wrappers rely on:
+    holds ``env``, forwards unknown attributes, ``step`` = ``step_async`` + ``step_wait``."""
+
+    def __init__(self, env):
+        self.env = env
+
+    def reset_async(self, **kwargs):
+        return self.env.reset_async(**kwargs)
+
+    def reset_wait(self, **kwargs):
+        return self.env.reset_wait(**kwargs)
+
+    def reset(self, **kwargs):
+        return self.env.reset(**kwargs)
+
+    def step_async(self, actions):
+        return self.env.step_async(actions)
+
+    def step_wait(self):
+        return self.env.step_wait()
+
+    def step(self, actions):
+        self.step_async(actions)
+        return self.step_wait()
+
+    def close(self, **kwargs):
+        return self.env.close(**kwargs)
+
+    def __getattr__(self, name):
+        if name.startswith("_") or name == "env":
+            raise AttributeError(name)
+        return getattr(self.env, name)
+
+    @property
+    def unwrapped(self):
+        return self.env.unwrapped
+
+
 def _install_stubs(root: str) -> None:
     if "gym" not in sys.modules:
         gym = types.ModuleType("gym")
@@ -106,7 +145,7 @@ def _install_stubs(root: str) -> None:
         gym.ActionWrapper = _Wrapper
         vector = types.ModuleType("gym.vector")
         vector.VectorEnv = type("VectorEnv", (), {})
-        vector.VectorEnvWrapper = type("VectorEnvWrapper", (), {})
+        vector.VectorEnvWrapper = _VectorEnvWrapper
         gym.vector = vector
         sys.modules.update({
             "gym": gym, "gym.spaces": spaces, "gym.envs": envs, "gym.wrappers": wrappers,
@@ -154,6 +193,24 @@ def load_reference():
     kuramoto = _load("pdegym.kuramoto.kuramoto", "pdegym/kuramoto/kuramoto.py")
     _CACHE["mods"] = (kuramoto, transforms)
     return _CACHE["mods"]
+
+
+def load_reference_wrappers():
+    """``(vec_wrappers module, transforms module)`` of the reference, executed where they lie.
+    ``vec_wrappers.py`` uses ``np.bool8``, which NumPy 2 removed; the alias is restored in the
+    NumPy namespace for the import (an environment shim, the reference file is untouched)."""
+    _, transforms = load_reference()
+    if "pdegym.common.vec_wrappers" not in sys.modules:
+        if not hasattr(np, "bool8"):
+            np.bool8 = np.bool_
+        import importlib.util
+
+        path = os.path.join(reference_root(), "pdegym", "common", "vec_wrappers.py")
+        spec = importlib.util.spec_from_file_location("pdegym.common.vec_wrappers", path)
+        mod = importlib.util.module_from_spec(spec)
+        sys.modules["pdegym.common.vec_wrappers"] = mod
+        spec.loader.exec_module(mod)
+    return sys.modules["pdegym.common.vec_wrappers"], transforms
 
 
 def make_reference_env(Xi=None, **config):

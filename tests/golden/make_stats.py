@@ -1,8 +1,10 @@
 """Long-horizon reference statistics for the 1 % gate (BASELINE.json north star: "energy spectrum
 and mean dissipation must agree within 1%").
 
-    python tests/golden/make_stats.py default 2048      # ~12 min on 8 cores
-    python tests/golden/make_stats.py large 384
+    python tests/golden/make_stats.py default 32768     # ~17 min on 8 cores
+    python tests/golden/make_stats.py large 4096
+
+(optionally with KS_ORACLE_LIB pointing at a -march=native build of oracle/ks_oracle.c)
 
 Protocol: every env starts from u ~ U(-0.4,0.4)^N, runs the reference's 800
 no-op burn-in periods, then one 400-period episode with i.i.d. actions ~ U(-1,1)^J; statistics are
@@ -49,7 +51,7 @@ def main():
     rew = np.zeros(E)
     for k in range(K):
         a = rng.uniform(-1, 1, (E, cfg.J)).astype(np.float32)
-        phi = ko.forcing(a, F)
+        phi = ks_c.forcing(a, F)            # == ko.forcing bit for bit (tests/test_oracle.py), much faster
         u, r = ks_c.step(cfg, u, phi)
         spec += ko.energy_spectrum(u)
         diss += ko.dissipation_rate(u, phi, cfg.dx)
