@@ -56,6 +56,10 @@ class KSVecEnv(VectorEnvBase):
                       auto-resets always use the device generator with a fresh OS seed (the
                       reference reseeds from OS entropy there, kuramoto.py:101).
     ``burnin_periods`` override of ``int(200/dt/cfg_steps)`` (= 800) no-op periods in ``reset``
+    ``reset_mode``    ``"burnin"`` (default, the reference's semantics: an auto-reset runs the burn-in
+                      launch before ``step`` returns) or ``"pool"``: auto-resets inject states that a
+                      side stream burned in ahead of time (``reset_pool.ResetPool``, ``pool_slots``
+                      batches in flight); explicit ``reset()`` calls always burn in synchronously.
     ``sensor_stride`` observation sampling fused into the kernel's output stage: observations are
                       ``u[..., stride//2::stride]`` as ``SensorTransform(stride)`` would return
                       (``pdegym/common/transforms.py:231-247``); 1 = full state, which is what the
@@ -69,7 +73,8 @@ class KSVecEnv(VectorEnvBase):
     def __init__(self, num_envs: int, config: Optional[dict] = None, *, Xi: Optional[Sequence[float]] = None,
                  device: Optional[int] = None, precision: str = "f64", reward_mode: Optional[str] = None,
                  ic: str = "numpy", burnin_periods: Optional[int] = None, points_per_lane: int = 0,
-                 sensor_stride: int = 1, copy: bool = True, **kwargs):
+                 sensor_stride: int = 1, copy: bool = True, reset_mode: str = "burnin", pool_slots: int = 2,
+                 **kwargs):
         cfg = dict(config or {})
         cfg.update(kwargs)
         self.L = float(cfg.pop("L", 22.0))
@@ -94,6 +99,9 @@ class KSVecEnv(VectorEnvBase):
         if ic not in ("numpy", "device"):
             raise ValueError("ic must be 'numpy' or 'device'")
         self.reward_mode, self.precision, self.ic, self.copy = reward_mode, precision, ic, copy
+        if reset_mode not in ("burnin", "pool"):
+            raise ValueError("reset_mode must be 'burnin' or 'pool'")
+        self.reset_mode, self._pool_slots, self._pool = reset_mode, int(pool_slots), None
         self.sensor_stride = int(sensor_stride)
         if not (1 <= self.sensor_stride <= self.N):
             raise ValueError("sensor_stride must be in [1, N]")
@@ -253,6 +261,22 @@ class KSVecEnv(VectorEnvBase):
                 self._h, None, None if mask_arr is None else mask_arr.ctypes.data, _lib.KS_HOST, dev_seed, K,
                 self._stream()))
 
+    def _auto_reset(self, mask) -> None:
+        """gym's per-sub-env auto-reset: burn-in launch (reference semantics) or pooled states."""
+        if self.reset_mode == "burnin":
+            self._reset_impl(None, None, mask, None)
+            return
+        if self._pool is None:
+            from .reset_pool import ResetPool
+
+            self._pool = ResetPool(self, slots=self._pool_slots)
+        batch, slot = self._pool.take()
+        m = None
+        if mask is not None:
+            m = torch.as_tensor(np.asarray(mask, dtype=np.uint8)).to(self.device)
+        _lib.check(self._h, self._lib.ks_reset(self._h, _ptr(batch), _ptr(m), _lib.KS_DEVICE, 0, 0, self._stream()))
+        self._pool.release(slot)
+
     def reset(self, seed: Optional[int] = None, return_info: bool = False, options: Optional[dict] = None,
               *, u0=None, burnin_periods: Optional[int] = None, **kwargs):
         """``KuramotoSivashinskyEnv.reset`` for every env (kuramoto.py:100-116): initial condition,
@@ -310,7 +334,7 @@ class KSVecEnv(VectorEnvBase):
                 finals[i] = u[i, self.sensor_stride // 2::self.sensor_stride].reshape(1, self.obs_len)
             infos["final_observation"] = finals
             infos["_final_observation"] = truncated.copy()
-            self._reset_impl(None, None, None if truncated.all() else truncated, None)
+            self._auto_reset(None if truncated.all() else truncated)
             u_new, _ = self.get_state()
             obs = np.array(obs)
             obs[truncated] = self._observe(u_new[truncated])
@@ -463,6 +487,9 @@ class KSVecEnv(VectorEnvBase):
 
     # ------------------------------------------------------------------ teardown
     def close_extras(self, **kwargs):
+        if getattr(self, "_pool", None) is not None:
+            self._pool.close()
+            self._pool = None
         if getattr(self, "_h", None) is not None:
             self._lib.ks_destroy(self._h)
             self._h = None

@@ -233,3 +233,40 @@ def test_reward_func_and_forcing_helpers():
     with pytest.raises(TypeError):
         d.reward_func(u)
     env.close(); d.close()
+
+
+def test_reset_pool_mode_injects_preburned_states():
+    """reset_mode="pool": the auto-reset takes a batch that the side stream burned in ahead of time
+    (same IC distribution, same 800-period burn-in, each state used once)."""
+    import torch
+    from model_based_pde_control_b200 import KSVecEnv
+
+    B = 16
+    env = KSVecEnv(B, dict(cfg_steps=10, Tmax=0.03), burnin_periods=6, reset_mode="pool", pool_slots=2, ic="device")
+    env.reset(seed=3)
+    a = np.zeros((B, 4), np.float32)
+    seen = []
+    for ep in range(4):                                    # 4 episode ends -> pool slots are recycled twice
+        for k in range(3):
+            obs, rew, term, trunc, info = env.step(a)
+        assert trunc.all() and (info["step"] == 3).all() and info["_final_observation"].all()
+        u, ts = env.get_state()
+        assert (ts == 0).all() and np.array_equal(obs[:, 0], u.astype(np.float32))
+        seen.append(u.copy())
+    assert env._pool is not None and env._pool.refills >= 2 + 4
+    for i in range(4):
+        for j in range(i):
+            assert not np.array_equal(seen[i], seen[j]), "every pooled batch must be fresh"
+    # a pooled state is exactly what reset_device(seed) + burn-in produces on an identical env
+    chk = KSVecEnv(B, dict(cfg_steps=10, Tmax=0.03), burnin_periods=6, ic="device")
+    pool = env._pool
+    first_seed = (pool._next_seed - pool.refills * 0x9E3779B97F4A7C15) & (2 ** 64 - 1)
+    chk.reset_device(seed=first_seed)
+    torch.cuda.synchronize()
+    assert np.array_equal(chk.get_state()[0], seen[0])
+    # partial truncation goes through the same path with a mask
+    env.set_state(seen[0], np.array([2] * 8 + [0] * 8, dtype=np.int32))
+    obs, rew, term, trunc, info = env.step(a)
+    u, ts = env.get_state()
+    assert trunc[:8].all() and not trunc[8:].any() and (ts[:8] == 0).all() and (ts[8:] == 1).all()
+    env.close(); chk.close()

@@ -44,7 +44,6 @@ def test_gpu_resident_rollout_matches_host_api_path():
         assert np.array_equal(batch.obs[t + 1, :, 0].cpu().numpy(), o)
         assert np.array_equal(batch.rewards[t].cpu().numpy(), r)
     # the truncating step: nxtobs is the FINAL observation, the next obs is post-reset
-    ref._h_act[:] = acts[4].cpu().numpy().reshape(B, 4)
     pre = ref.get_state()[0]
     chk = KSVecEnv(B, cfg)
     chk.set_state(pre, 4)
