@@ -192,6 +192,9 @@ def run_gpu_arm(args):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        # stdout carries exactly ONE JSON line: anything NCCL prints (e.g. its version banner when
+        # NCCL_DEBUG=VERSION/INFO) goes to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
 
     B = args.envs_per_gpu
