@@ -36,13 +36,22 @@
 extern "C" {
 #endif
 
-#define KS_ABI_VERSION 1
+#define KS_ABI_VERSION 2
 
 enum ks_precision { KS_F64 = 0, KS_F32 = 1 };
 /* KS_REWARD_L2: what the reference executes, -(1/N)*||u||^2 (kuramoto.py:64-65,72).
  * KS_REWARD_DISSIPATION: the intended -(mean(uxx^2)+mean(ux^2)+mean(u*phi)) (kuramoto.py:67-70). */
 enum ks_reward_mode { KS_REWARD_L2 = 0, KS_REWARD_DISSIPATION = 1 };
 enum ks_where { KS_HOST = 0, KS_DEVICE = 1 };
+/* KS_SOLVER_FD_RK4: the reference's scheme -- periodic finite differences + classic RK4
+ *   (kuramoto.py:83-90,118-129); the parity path (<= 1e-10 against the reference).
+ * KS_SOLVER_ETDRK4: pseudo-spectral exponential integrator (Cox & Matthews 2002; contour-integral
+ *   coefficients after Kassam & Trefethen 2005, precomputed on the host in ks_create), hand-written
+ *   in-register / warp-level FFT.  NOT in the reference: it integrates the same equation
+ *   (kuramoto.py:127) with a different discretisation, `dt` and `cfg_steps` are then the ETDRK4
+ *   step and the steps per control period (e.g. dt = 0.025, cfg_steps = 10 for the reference's
+ *   0.25 time units).  N = 64 and KS_REWARD_L2 only. */
+enum ks_solver { KS_SOLVER_FD_RK4 = 0, KS_SOLVER_ETDRK4 = 1 };
 
 enum ks_error {
     KS_OK = 0,
@@ -67,6 +76,8 @@ typedef struct ks_config {
     int32_t points_per_lane;   /* 0 = choose automatically; else P with N % P == 0, 4<=P<=16 */
     int32_t obs_stride;        /* SensorTransform stride s: obs = u[s/2::s] (transforms.py:236-239);
                                   0 or 1 = full state (what the MBRL loop uses, mbrl.py:171,174) */
+    int32_t solver;            /* enum ks_solver; 0 = the reference's FD-RK4 scheme */
+    int32_t dealias;           /* KS_SOLVER_ETDRK4 only: 1 = 2/3-rule dealiasing of (u^2)_x, 0 = none */
     double L;                  /* domain length (22.0) */
     double dt;                 /* RK4 step (1e-3) */
     const float *forcing;      /* host, [J*N] row-major float32: GaussianForcing.forcing

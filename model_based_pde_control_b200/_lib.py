@@ -12,14 +12,17 @@ import os
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG_DIR, "libks_b200.so")
 
-KS_ABI_VERSION = 1
+KS_ABI_VERSION = 2
 KS_F64, KS_F32 = 0, 1
 KS_REWARD_L2, KS_REWARD_DISSIPATION = 0, 1
 KS_HOST, KS_DEVICE = 0, 1
+KS_SOLVER_FD_RK4, KS_SOLVER_ETDRK4 = 0, 1
 KS_ERR_ARG, KS_ERR_UNSUPPORTED, KS_ERR_NO_DEVICE, KS_ERR_STATE = -1, -2, -3, -4
 
 PRECISIONS = {"f64": KS_F64, "fp64": KS_F64, "float64": KS_F64, "f32": KS_F32, "fp32": KS_F32, "float32": KS_F32}
 REWARD_MODES = {"l2": KS_REWARD_L2, "dissipation": KS_REWARD_DISSIPATION}
+SOLVERS = {"fd_rk4": KS_SOLVER_FD_RK4, "rk4": KS_SOLVER_FD_RK4, "reference": KS_SOLVER_FD_RK4,
+           "etdrk4": KS_SOLVER_ETDRK4, "spectral": KS_SOLVER_ETDRK4}
 
 
 class KsConfig(ctypes.Structure):
@@ -38,6 +41,8 @@ class KsConfig(ctypes.Structure):
         ("device", ctypes.c_int32),
         ("points_per_lane", ctypes.c_int32),
         ("obs_stride", ctypes.c_int32),
+        ("solver", ctypes.c_int32),
+        ("dealias", ctypes.c_int32),
         ("L", ctypes.c_double),
         ("dt", ctypes.c_double),
         ("forcing", ctypes.c_void_p),

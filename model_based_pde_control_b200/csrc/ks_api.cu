@@ -4,12 +4,15 @@
 #include "../../include/ks_b200.h"
 
 #include <cmath>
+#include <complex>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
 #include <new>
+#include <vector>
 
 #include "ks_dispatch.h"
+#include "ks_etd.cuh"
 
 namespace {
 
@@ -53,6 +56,7 @@ struct ks_handle {
     uint8_t *out = nullptr;     // packed output block
     double *scratch64 = nullptr;  // [B,N] f64 staging for set/get_state in F32 mode and host ICs
     uint8_t *mask = nullptr;      // [B] staging for host reset masks
+    void *etd_tables = nullptr;   // [kEtdTables][N] T: ETDRK4 coefficient tables (spectral solver only)
     size_t out_off[5] = {0, 0, 0, 0, 0}, out_total = 0;
     uint64_t launches = 0;
     char err[256] = "";
@@ -95,6 +99,45 @@ void fill_coef(ks::Coef<T> &c, double dx, double dt)
     c.dt_half = (T)(dt / 2.0);
     c.dt_full = (T)dt;
     c.dt_sixth = (T)(dt / 6.0);
+}
+
+// ETDRK4 coefficient tables for the spectral solver, natural FFT order, float64 on the host.
+//   L(k) = k^2 - k^4;  E = exp(hL), E2 = exp(hL/2);  Q, f1, f2, f3 = the phi-function combinations
+//   of Cox & Matthews (2002) eqs. 26-29, evaluated as means over M = 32 points of the upper unit
+//   half-circle around hL (Kassam & Trefethen 2005, section 3 -- avoids the cancellation of the
+//   closed forms near L = 0);  g = -k/2 * dealias / N multiplies i*FFT(u^2)  (the 1/N makes the
+//   unnormalised transform pair of the kernel an identity).
+// Order of the tables: ks::kTabE, kTabE2, kTabQ, kTabQ2 (= 2Q), kTabF1, kTabF22 (= 2 f2), kTabF3, kTabG.
+void etd_tables_host(int N, double L, double h, bool dealias, std::vector<double> &out)
+{
+    constexpr int M = 32;
+    const double pi = 3.14159265358979323846;
+    out.assign((size_t)ks::kEtdTables * N, 0.0);
+    for (int i = 0; i < N; ++i) {
+        const int m = i < N / 2 ? i : i - N;                 // -N/2 .. N/2-1 (fftfreq order)
+        const double k_even = 2.0 * pi / L * m;
+        const double k_odd = (N % 2 == 0 && i == N / 2) ? 0.0 : k_even;   // odd derivative of the Nyquist mode = 0
+        const double k2 = k_even * k_even, lin = k2 - k2 * k2;
+        std::complex<double> sq(0, 0), s1(0, 0), s2(0, 0), s3(0, 0);
+        for (int j = 1; j <= M; ++j) {
+            const std::complex<double> r = std::polar(1.0, pi * (j - 0.5) / M);
+            const std::complex<double> z = h * lin + r, ez = std::exp(z), z3 = z * z * z;
+            sq += (std::exp(z / 2.0) - 1.0) / z;
+            s1 += (-4.0 - z + ez * (4.0 - 3.0 * z + z * z)) / z3;
+            s2 += (2.0 + z + ez * (-2.0 + z)) / z3;
+            s3 += (-4.0 - 3.0 * z - z * z + ez * (4.0 - z)) / z3;
+        }
+        const double Q = h * sq.real() / M, f1 = h * s1.real() / M, f2 = h * s2.real() / M, f3 = h * s3.real() / M;
+        const bool keep = !dealias || (m < 0 ? -m : m) <= N / 3;           // 2/3 rule
+        out[(size_t)ks::kTabE * N + i] = std::exp(h * lin);
+        out[(size_t)ks::kTabE2 * N + i] = std::exp(h * lin / 2.0);
+        out[(size_t)ks::kTabQ * N + i] = Q;
+        out[(size_t)ks::kTabQ2 * N + i] = 2.0 * Q;
+        out[(size_t)ks::kTabF1 * N + i] = f1;
+        out[(size_t)ks::kTabF22 * N + i] = 2.0 * f2;
+        out[(size_t)ks::kTabF3 * N + i] = f3;
+        out[(size_t)ks::kTabG * N + i] = keep ? -0.5 * k_odd / N : 0.0;
+    }
 }
 
 // Points per lane P for a grid of N points and a batch of B envs (lanes = N / P must fit one warp).
@@ -266,6 +309,15 @@ int launch_period(ks_handle *h, int K, const float *actions, const float *phi, f
     p.obs_len = h->obs_len;
     p.inv_cfg_steps = 1.0 / h->cfg.cfg_steps;
     p.inv_N = 1.0 / h->cfg.N;
+    if (h->cfg.solver == KS_SOLVER_ETDRK4) {
+        ks::EtdParams ep;
+        ep.p = p;
+        ep.tables = h->etd_tables;
+        void *eargs[1] = {&ep};
+        KS_CUDA(h, cudaLaunchKernel(h->kernel, dim3(h->grid), dim3(ks::kBlockThreads), eargs, 0, stream));
+        h->launches += 1;
+        return KS_OK;
+    }
     void *args[2] = {&p, h->cfg.precision == KS_F64 ? (void *)&h->c64 : (void *)&h->c32};
     KS_CUDA(h, cudaLaunchKernel(h->kernel, dim3(h->grid), dim3(ks::kBlockThreads), args, 0, stream));
     h->launches += 1;
@@ -298,7 +350,14 @@ int ks_create(const ks_config *cfg, ks_handle **out)
     if (cfg->reward_mode != KS_REWARD_L2 && cfg->reward_mode != KS_REWARD_DISSIPATION)
         return fail(nullptr, KS_ERR_ARG, "ks_create: bad reward_mode");
 
-    int P = cfg->points_per_lane;
+    if (cfg->solver != KS_SOLVER_FD_RK4 && cfg->solver != KS_SOLVER_ETDRK4)
+        return fail(nullptr, KS_ERR_ARG, "ks_create: bad solver %d", cfg->solver);
+    const bool etd = cfg->solver == KS_SOLVER_ETDRK4;
+    if (etd && (cfg->N != ks::kEtdN || cfg->reward_mode != KS_REWARD_L2))
+        return fail(nullptr, KS_ERR_UNSUPPORTED, "ks_create: the spectral ETDRK4 solver supports N = %d and the L2 reward only "
+                    "(N=%d reward_mode=%d)", ks::kEtdN, cfg->N, cfg->reward_mode);
+
+    int P = etd ? 8 : cfg->points_per_lane;
     if (P != 0 && (P < ks::kMinP || P > ks::kMaxP || cfg->N % P || cfg->N / P > 32))
         return fail(nullptr, KS_ERR_UNSUPPORTED,
                     "ks_create: N=%d needs N = lanes*P with 4<=P<=16, lanes<=32 (points_per_lane=%d)", cfg->N,
@@ -337,6 +396,13 @@ int ks_create(const ks_config *cfg, ks_handle **out)
     const bool f64 = cfg->precision == KS_F64, l2 = cfg->reward_mode == KS_REWARD_L2;
     h->kernel = f64 ? (l2 ? ks::period_kernel_f64_l2(P) : ks::period_kernel_f64_diss(P))
                     : (l2 ? ks::period_kernel_f32_l2(P) : ks::period_kernel_f32_diss(P));
+    if (etd) {
+        // a pair of envs per 8 lanes x 8 complex registers, 8 envs per warp (ks_etd.cuh)
+        h->lanes = 8;
+        h->envs_per_warp = 8;
+        h->grid = (int)((cfg->num_envs + 8 * (ks::kBlockThreads / 32) - 1) / (8 * (ks::kBlockThreads / 32)));
+        h->kernel = f64 ? ks::etd_kernel_f64() : ks::etd_kernel_f32();
+    }
     const double dx = cfg->L / cfg->N;  // kuramoto.py:55
     fill_coef(h->c64, dx, cfg->dt);
     fill_coef(h->c32, dx, cfg->dt);
@@ -371,6 +437,17 @@ int ks_create(const ks_config *cfg, ks_handle **out)
         KS_TRY(cudaMemset(h->nonfinite, 0, B));
         KS_TRY(cudaMemset(h->out, 0, h->out_total));
         KS_TRY(cudaMemcpy(h->F, cfg->forcing, J * N * sizeof(float), cudaMemcpyHostToDevice));
+        if (etd) {
+            std::vector<double> tab;
+            etd_tables_host(cfg->N, cfg->L, cfg->dt, cfg->dealias != 0, tab);
+            KS_TRY(cudaMalloc(&h->etd_tables, tab.size() * esz));
+            if (f64) {
+                KS_TRY(cudaMemcpy(h->etd_tables, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice));
+            } else {
+                std::vector<float> tab32(tab.begin(), tab.end());
+                KS_TRY(cudaMemcpy(h->etd_tables, tab32.data(), tab32.size() * sizeof(float), cudaMemcpyHostToDevice));
+            }
+        }
 #undef KS_TRY
     } while (0);
     if (rc != KS_OK) {
@@ -394,6 +471,7 @@ int ks_destroy(ks_handle *h)
         cudaFree(h->out);
         cudaFree(h->scratch64);
         cudaFree(h->mask);
+        cudaFree(h->etd_tables);
         cudaGetLastError();
     }
     delete h;

@@ -60,6 +60,14 @@ class KSVecEnv(VectorEnvBase):
                       launch before ``step`` returns) or ``"pool"``: auto-resets inject states that a
                       side stream burned in ahead of time (``reset_pool.ResetPool``, ``pool_slots``
                       batches in flight); explicit ``reset()`` calls always burn in synchronously.
+    ``solver``        ``"fd_rk4"`` (default): the reference's own scheme -- periodic finite differences +
+                      classic RK4 (kuramoto.py:83-90,118-129), the parity path.  ``"etdrk4"``: the
+                      pseudo-spectral exponential integrator the north star names (Cox & Matthews
+                      2002, Kassam & Trefethen 2005; hand-written FFT kernel, N = 64, L2 reward).  It
+                      is NOT the reference's discretisation (states differ by ~2e-3 per control
+                      period at the default grid); ``dt`` / ``cfg_steps`` are then the ETDRK4 step
+                      and the steps per period, e.g. ``dt=0.025, cfg_steps=10`` for the reference's
+                      0.25 time units per control period.  ``dealias`` = 2/3 rule on ``(u^2)_x``.
     ``sensor_stride`` observation sampling fused into the kernel's output stage: observations are
                       ``u[..., stride//2::stride]`` as ``SensorTransform(stride)`` would return
                       (``pdegym/common/transforms.py:231-247``); 1 = full state, which is what the
@@ -74,7 +82,7 @@ class KSVecEnv(VectorEnvBase):
                  device: Optional[int] = None, precision: str = "f64", reward_mode: Optional[str] = None,
                  ic: str = "numpy", burnin_periods: Optional[int] = None, points_per_lane: int = 0,
                  sensor_stride: int = 1, copy: bool = True, reset_mode: str = "burnin", pool_slots: int = 2,
-                 **kwargs):
+                 solver: str = "fd_rk4", dealias: bool = True, **kwargs):
         cfg = dict(config or {})
         cfg.update(kwargs)
         self.L = float(cfg.pop("L", 22.0))
@@ -96,6 +104,9 @@ class KSVecEnv(VectorEnvBase):
             raise ValueError(f"reward_mode must be one of {sorted(_lib.REWARD_MODES)}")
         if precision not in _lib.PRECISIONS:
             raise ValueError(f"precision must be one of {sorted(_lib.PRECISIONS)}")
+        if solver not in _lib.SOLVERS:
+            raise ValueError(f"solver must be one of {sorted(_lib.SOLVERS)}")
+        self.solver, self.dealias = solver, bool(dealias)
         if ic not in ("numpy", "device"):
             raise ValueError("ic must be 'numpy' or 'device'")
         self.reward_mode, self.precision, self.ic, self.copy = reward_mode, precision, ic, copy
@@ -133,7 +144,8 @@ class KSVecEnv(VectorEnvBase):
             abi_version=_lib.KS_ABI_VERSION, num_envs=num_envs, N=self.N, J=self.J, cfg_steps=self.cfg_steps,
             max_episode_steps=self.max_episode_steps, burnin_periods=self.burnin_periods,
             precision=_lib.PRECISIONS[precision], reward_mode=_lib.REWARD_MODES[reward_mode],
-            device=self.device_index, points_per_lane=points_per_lane, obs_stride=self.sensor_stride, L=self.L, dt=self.dt,
+            device=self.device_index, points_per_lane=points_per_lane, obs_stride=self.sensor_stride,
+            solver=_lib.SOLVERS[solver], dealias=int(self.dealias), L=self.L, dt=self.dt,
             forcing=self._F_host.ctypes.data)
         handle = ctypes.c_void_p()
         torch.cuda.init()
