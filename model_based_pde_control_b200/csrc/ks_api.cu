@@ -105,9 +105,10 @@ void fill_coef(ks::Coef<T> &c, double dx, double dt)
 //   L(k) = k^2 - k^4;  E = exp(hL), E2 = exp(hL/2);  Q, f1, f2, f3 = the phi-function combinations
 //   of Cox & Matthews (2002) eqs. 26-29, evaluated as means over M = 32 points of the upper unit
 //   half-circle around hL (Kassam & Trefethen 2005, section 3 -- avoids the cancellation of the
-//   closed forms near L = 0);  g = -k/2 * dealias / N multiplies i*FFT(u^2)  (the 1/N makes the
-//   unnormalised transform pair of the kernel an identity).
-// Order of the tables: ks::kTabE, kTabE2, kTabQ, kTabQ2 (= 2Q), kTabF1, kTabF22 (= 2 f2), kTabF3, kTabG.
+//   closed forms near L = 0);  g = -k/2 * dealias multiplies i*FFT(u^2).
+// The kernel carries the nonlinear terms pre-multiplied by Q, so the tables it gets are
+//   E, E2, f1/Q, 2 f2/Q, f3/Q, Q g / N, Q / N   (ks::kTabE ... kTabQN; the 1/N makes the kernel's
+//   unnormalised transform pair an identity).
 void etd_tables_host(int N, double L, double h, bool dealias, std::vector<double> &out)
 {
     constexpr int M = 32;
@@ -131,12 +132,11 @@ void etd_tables_host(int N, double L, double h, bool dealias, std::vector<double
         const bool keep = !dealias || (m < 0 ? -m : m) <= N / 3;           // 2/3 rule
         out[(size_t)ks::kTabE * N + i] = std::exp(h * lin);
         out[(size_t)ks::kTabE2 * N + i] = std::exp(h * lin / 2.0);
-        out[(size_t)ks::kTabQ * N + i] = Q;
-        out[(size_t)ks::kTabQ2 * N + i] = 2.0 * Q;
-        out[(size_t)ks::kTabF1 * N + i] = f1;
-        out[(size_t)ks::kTabF22 * N + i] = 2.0 * f2;
-        out[(size_t)ks::kTabF3 * N + i] = f3;
-        out[(size_t)ks::kTabG * N + i] = keep ? -0.5 * k_odd / N : 0.0;
+        out[(size_t)ks::kTabR1 * N + i] = f1 / Q;
+        out[(size_t)ks::kTabR22 * N + i] = 2.0 * f2 / Q;
+        out[(size_t)ks::kTabR3 * N + i] = f3 / Q;
+        out[(size_t)ks::kTabG * N + i] = keep ? Q * (-0.5 * k_odd) / N : 0.0;
+        out[(size_t)ks::kTabQN * N + i] = Q / N;
     }
 }
 

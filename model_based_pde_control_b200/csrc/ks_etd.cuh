@@ -21,8 +21,8 @@
 //     twiddle by W64^(l r), 8x8 transpose inside the 8-lane group, radix-8 butterflies in
 //     registers.  The inverse runs the same steps backwards, so no bit reversal is ever needed.
 //   * the transpose goes through a warp-private, padded shared-memory tile (128-bit, conflict-free
-//     both ways, only __syncwarp); the per-wavenumber tables and the period's forcing spectrum
-//     live in shared memory as well; the state, the stage values and the twiddles in registers.
+//     both ways, only __syncwarp); the per-wavenumber tables live in shared memory as well; the
+//     state, the stage values, the twiddles and the period's forcing spectrum in registers.
 //   * HBM is touched at control-period boundaries only (state in, state / observation / reward out).
 #pragma once
 
@@ -31,8 +31,12 @@
 namespace ks {
 
 constexpr int kEtdN = 64;          // grid points handled by this kernel
-constexpr int kEtdTables = 8;      // E, E2, Q, 2Q, f1, 2 f2, f3, g/N   (each [N], natural FFT order)
-enum { kTabE = 0, kTabE2, kTabQ, kTabQ2, kTabF1, kTabF22, kTabF3, kTabG };
+// Per-wavenumber tables, each [N] in natural FFT order (host-precomputed, ks_api.cu).  The kernel
+// carries the nonlinear terms pre-multiplied by Q (N~ = Q N), which removes Q from the stage
+// formulas; the final combination then needs f1/Q, 2 f2/Q, f3/Q (Q = h phi_1(hL/2)/2 > 0).
+constexpr int kEtdTables = 7;
+enum { kTabE = 0, kTabE2, kTabR1 /* f1/Q */, kTabR22 /* 2 f2/Q */, kTabR3 /* f3/Q */, kTabG /* Q g / N */,
+       kTabQN /* Q / N */ };
 
 template <typename T>
 struct __align__(2 * sizeof(T)) C2 {
@@ -126,25 +130,21 @@ __device__ __forceinline__ void ifft64(T (&x)[8], T (&y)[8], const T (&twx)[8], 
     fft8<T>(y, x);
 }
 
-// One table row for this lane: 8 values (registers m = 0..7), stored as pairs so that a lane reads
-// four 2-element vectors.  Layout in shared memory: [table][m/2][lane j][m&1].
+// Table values for this lane's registers m = 2h, 2h+1 (k = 8 m + j), one 2-element vector load.
+// Layout in shared memory: [table][h][lane j].
 template <typename T>
-__device__ __forceinline__ void load_table(const C2<T> *tab, int which, int l, T (&t)[8])
+__device__ __forceinline__ C2<T> tab2(const C2<T> *tab, int which, int h, int l)
 {
-#pragma unroll
-    for (int h = 0; h < 4; ++h) {
-        const C2<T> v = tab[(which * 4 + h) * 8 + l];
-        t[2 * h] = v.x;
-        t[2 * h + 1] = v.y;
-    }
+    return tab[(which * 4 + h) * 8 + l];
 }
 
-// Spectral right-hand side without the linear part, in place:
-//   w <- i g/N * FFT( (Re/Im IFFT(w))^2 ) + phi_hat            (both packed fields at once)
+// Spectral right-hand side without the linear part, pre-multiplied by Q, in place:
+//   w <- i (Q g / N) * FFT( (Re/Im IFFT(w))^2 ) + Q phi_hat / N        (both packed fields at once)
 // With FIRST the squares of the physical values are the pre-step reward terms (kuramoto.py:84).
 template <typename T, bool FIRST>
 __device__ __forceinline__ void nonlinear(T (&wx)[8], T (&wy)[8], const T (&twx)[8], const T (&twy)[8], C2<T> *tile,
-                                          const C2<T> *tab, const C2<T> *phih, int l, int lane, T &racc_a, T &racc_b)
+                                          const C2<T> *tab, const T (&phx)[8], const T (&phy)[8], int l, T &racc_a,
+                                          T &racc_b)
 {
     ifft64<T>(wx, wy, twx, twy, tile, l);
 #pragma unroll
@@ -157,14 +157,14 @@ __device__ __forceinline__ void nonlinear(T (&wx)[8], T (&wy)[8], const T (&twx)
         racc_b += ((wy[0] + wy[1]) + (wy[2] + wy[3])) + ((wy[4] + wy[5]) + (wy[6] + wy[7]));
     }
     fft64<T>(wx, wy, twx, twy, tile, l);
-    T g[8];
-    load_table<T>(tab, kTabG, l, g);
 #pragma unroll
-    for (int m = 0; m < 8; ++m) {
-        const C2<T> f = phih[m * 32 + lane];
-        const T re = wx[m], im = wy[m];
-        wx[m] = fma_t<T>(-g[m], im, f.x);
-        wy[m] = fma_t<T>(g[m], re, f.y);
+    for (int h = 0; h < 4; ++h) {
+        const C2<T> g = tab2<T>(tab, kTabG, h, l);
+        const T re0 = wx[2 * h], im0 = wy[2 * h], re1 = wx[2 * h + 1], im1 = wy[2 * h + 1];
+        wx[2 * h] = fma_t<T>(-g.x, im0, phx[2 * h]);
+        wy[2 * h] = fma_t<T>(g.x, re0, phy[2 * h]);
+        wx[2 * h + 1] = fma_t<T>(-g.y, im1, phx[2 * h + 1]);
+        wy[2 * h + 1] = fma_t<T>(g.y, re1, phy[2 * h + 1]);
     }
 }
 
@@ -184,7 +184,6 @@ __global__ void __launch_bounds__(kBlockThreads) ks_etd_kernel(const EtdParams e
     constexpr int kWarps = kBlockThreads / 32;
     __shared__ C2<T> s_tab[kEtdTables * 4 * 8];
     __shared__ C2<T> s_tile[kWarps][4 * 72];
-    __shared__ C2<T> s_phih[kWarps][8 * 32];
 
     // per-wavenumber tables -> shared memory in register-pair layout (k = 8 m + j)
     {
@@ -210,7 +209,6 @@ __global__ void __launch_bounds__(kBlockThreads) ks_etd_kernel(const EtdParams e
     if (__ballot_sync(kFullMask, actA || actB) == 0u) return;   // warp-uniform (after the only __syncthreads)
 
     C2<T> *tile = &s_tile[wib][grp * 72];
-    C2<T> *phih = &s_phih[wib][0];
     const C2<T> *tab = s_tab;
 
     // twiddles W64^(l r) = exp(-2 pi i l r / 64)
@@ -238,8 +236,9 @@ __global__ void __launch_bounds__(kBlockThreads) ks_etd_kernel(const EtdParams e
 
     for (int k = 0; k < p.K; ++k) {
         // ---- jet forcing of this period: float32 FMA chain (transforms.py:262-265), then its spectrum
+        T phx[8], phy[8];      // Q phi_hat / N, kept in registers for the whole period
         {
-            T fx[8], fy[8];
+            T (&fx)[8] = phx, (&fy)[8] = phy;
             if (p.phi != nullptr) {
 #pragma unroll
                 for (int r = 0; r < 8; ++r) {
@@ -272,8 +271,11 @@ __global__ void __launch_bounds__(kBlockThreads) ks_etd_kernel(const EtdParams e
             }
             fft64<T>(fx, fy, twx, twy, tile, l);
 #pragma unroll
-            for (int m = 0; m < 8; ++m) phih[m * 32 + lane] = C2<T>{fx[m] * invN, fy[m] * invN};
-            __syncwarp();
+            for (int h = 0; h < 4; ++h) {
+                const C2<T> qn = tab2<T>(tab, kTabQN, h, l);
+                fx[2 * h] *= qn.x; fy[2 * h] *= qn.x;
+                fx[2 * h + 1] *= qn.y; fy[2 * h + 1] *= qn.y;
+            }
         }
 
         // ---- spectrum of the state, normalised: v = FFT(u) / N
@@ -284,70 +286,73 @@ __global__ void __launch_bounds__(kBlockThreads) ks_etd_kernel(const EtdParams e
 #pragma unroll
         for (int m = 0; m < 8; ++m) { vx[m] *= invN; vy[m] *= invN; }
 
-        // ---- cfg_steps ETDRK4 steps (Cox & Matthews 2002, eqs. 26-29)
+        // ---- cfg_steps ETDRK4 steps (Cox & Matthews 2002, eqs. 26-29), with N~ = Q N:
+        //   a = E2 v + N~v          b = E2 v + N~a = (a - N~v) + N~a          c = E2 a + 2 N~b - N~v
+        //   v' = E v + (f1/Q) N~v + (2 f2/Q) (N~a + N~b) + (f3/Q) N~c
         T racc_a = T(0), racc_b = T(0), dummy = T(0);
         for (int s = 0; s < p.cfg_steps; ++s) {
-            T nx[8], ny[8], ax[8], ay[8], wx[8], wy[8], t1[8], t2[8];
-            // Nv = N(v)
+            T nx[8], ny[8], ax[8], ay[8], wx[8], wy[8];
+            // N~v
 #pragma unroll
             for (int m = 0; m < 8; ++m) { nx[m] = vx[m]; ny[m] = vy[m]; }
-            nonlinear<T, true>(nx, ny, twx, twy, tile, tab, phih, l, lane, racc_a, racc_b);
-            // a = E2 v + Q Nv
-            load_table<T>(tab, kTabE2, l, t1);
-            load_table<T>(tab, kTabQ, l, t2);
+            nonlinear<T, true>(nx, ny, twx, twy, tile, tab, phx, phy, l, racc_a, racc_b);
+            // a = E2 v + N~v
 #pragma unroll
-            for (int m = 0; m < 8; ++m) {
-                ax[m] = fma_t<T>(t2[m], nx[m], t1[m] * vx[m]);
-                ay[m] = fma_t<T>(t2[m], ny[m], t1[m] * vy[m]);
-                wx[m] = ax[m];
-                wy[m] = ay[m];
-            }
-            // Na = N(a)
-            nonlinear<T, false>(wx, wy, twx, twy, tile, tab, phih, l, lane, dummy, dummy);
-            // b = E2 v + Q Na (-> w);  a <- E2 a - Q Nv;  v <- E v + f1 Nv + 2 f2 Na
-            load_table<T>(tab, kTabE2, l, t1);
-            load_table<T>(tab, kTabQ, l, t2);
+            for (int h = 0; h < 4; ++h) {
+                const C2<T> e2 = tab2<T>(tab, kTabE2, h, l);
 #pragma unroll
-            for (int m = 0; m < 8; ++m) {
-                const T nax = wx[m], nay = wy[m];
-                wx[m] = fma_t<T>(t2[m], nax, t1[m] * vx[m]);
-                wy[m] = fma_t<T>(t2[m], nay, t1[m] * vy[m]);
-                ax[m] = fma_t<T>(-t2[m], nx[m], t1[m] * ax[m]);
-                ay[m] = fma_t<T>(-t2[m], ny[m], t1[m] * ay[m]);
-                // stash Na in (nx, ny) is not possible yet: Nv is still needed for v below
-                t1[m] = nax;   // reuse the table registers for Na (tables are re-read below)
-                t2[m] = nay;
-            }
-            {
-                T e[8], f1[8], f22[8];
-                load_table<T>(tab, kTabE, l, e);
-                load_table<T>(tab, kTabF1, l, f1);
-                load_table<T>(tab, kTabF22, l, f22);
-#pragma unroll
-                for (int m = 0; m < 8; ++m) {
-                    vx[m] = fma_t<T>(f22[m], t1[m], fma_t<T>(f1[m], nx[m], e[m] * vx[m]));
-                    vy[m] = fma_t<T>(f22[m], t2[m], fma_t<T>(f1[m], ny[m], e[m] * vy[m]));
+                for (int q = 0; q < 2; ++q) {
+                    const int m = 2 * h + q;
+                    const T c = q ? e2.y : e2.x;
+                    wx[m] = ax[m] = fma_t<T>(c, vx[m], nx[m]);
+                    wy[m] = ay[m] = fma_t<T>(c, vy[m], ny[m]);
                 }
             }
-            // Nb = N(b)
-            nonlinear<T, false>(wx, wy, twx, twy, tile, tab, phih, l, lane, dummy, dummy);
-            // c = (E2 a - Q Nv) + 2 Q Nb (-> w);  v += 2 f2 Nb
-            load_table<T>(tab, kTabQ2, l, t1);
-            load_table<T>(tab, kTabF22, l, t2);
+            // N~a
+            nonlinear<T, false>(wx, wy, twx, twy, tile, tab, phx, phy, l, dummy, dummy);
+            // b = (a - N~v) + N~a (-> w);   a <- E2 a - N~v;   v <- E v + (f1/Q) N~v + (2 f2/Q) N~a
 #pragma unroll
-            for (int m = 0; m < 8; ++m) {
-                vx[m] = fma_t<T>(t2[m], wx[m], vx[m]);
-                vy[m] = fma_t<T>(t2[m], wy[m], vy[m]);
-                wx[m] = fma_t<T>(t1[m], wx[m], ax[m]);
-                wy[m] = fma_t<T>(t1[m], wy[m], ay[m]);
+            for (int h = 0; h < 4; ++h) {
+                const C2<T> e2 = tab2<T>(tab, kTabE2, h, l), e = tab2<T>(tab, kTabE, h, l);
+                const C2<T> r1 = tab2<T>(tab, kTabR1, h, l), r22 = tab2<T>(tab, kTabR22, h, l);
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    const int m = 2 * h + q;
+                    const T ce2 = q ? e2.y : e2.x, ce = q ? e.y : e.x, c1 = q ? r1.y : r1.x, c22 = q ? r22.y : r22.x;
+                    const T nax = wx[m], nay = wy[m];
+                    wx[m] = (ax[m] - nx[m]) + nax;
+                    wy[m] = (ay[m] - ny[m]) + nay;
+                    ax[m] = fma_t<T>(ce2, ax[m], -nx[m]);
+                    ay[m] = fma_t<T>(ce2, ay[m], -ny[m]);
+                    vx[m] = fma_t<T>(c22, nax, fma_t<T>(c1, nx[m], ce * vx[m]));
+                    vy[m] = fma_t<T>(c22, nay, fma_t<T>(c1, ny[m], ce * vy[m]));
+                }
             }
-            // Nc = N(c);  v += f3 Nc
-            nonlinear<T, false>(wx, wy, twx, twy, tile, tab, phih, l, lane, dummy, dummy);
-            load_table<T>(tab, kTabF3, l, t1);
+            // N~b
+            nonlinear<T, false>(wx, wy, twx, twy, tile, tab, phx, phy, l, dummy, dummy);
+            // v += (2 f2/Q) N~b;   c = (E2 a - N~v) + 2 N~b (-> w)
 #pragma unroll
-            for (int m = 0; m < 8; ++m) {
-                vx[m] = fma_t<T>(t1[m], wx[m], vx[m]);
-                vy[m] = fma_t<T>(t1[m], wy[m], vy[m]);
+            for (int h = 0; h < 4; ++h) {
+                const C2<T> r22 = tab2<T>(tab, kTabR22, h, l);
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    const int m = 2 * h + q;
+                    const T c22 = q ? r22.y : r22.x;
+                    vx[m] = fma_t<T>(c22, wx[m], vx[m]);
+                    vy[m] = fma_t<T>(c22, wy[m], vy[m]);
+                    wx[m] = fma_t<T>(T(2), wx[m], ax[m]);
+                    wy[m] = fma_t<T>(T(2), wy[m], ay[m]);
+                }
+            }
+            // N~c;   v += (f3/Q) N~c
+            nonlinear<T, false>(wx, wy, twx, twy, tile, tab, phx, phy, l, dummy, dummy);
+#pragma unroll
+            for (int h = 0; h < 4; ++h) {
+                const C2<T> r3 = tab2<T>(tab, kTabR3, h, l);
+                vx[2 * h] = fma_t<T>(r3.x, wx[2 * h], vx[2 * h]);
+                vy[2 * h] = fma_t<T>(r3.x, wy[2 * h], vy[2 * h]);
+                vx[2 * h + 1] = fma_t<T>(r3.y, wx[2 * h + 1], vx[2 * h + 1]);
+                vy[2 * h + 1] = fma_t<T>(r3.y, wy[2 * h + 1], vy[2 * h + 1]);
             }
         }
 

@@ -27,6 +27,9 @@ def main():
     ap.add_argument("--precision", default="f64")
     ap.add_argument("--reward-mode", default="l2")
     ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--solver", default="fd_rk4")
+    ap.add_argument("--dt", type=float, default=None)
+    ap.add_argument("--cfg-steps", type=int, default=None)
     ap.add_argument("--rollout", type=int, default=0, help="K periods per launch (0 = one launch per period)")
     args = ap.parse_args()
     dev = torch.device("cuda", 0)
@@ -34,7 +37,12 @@ def main():
         for P in [int(x) for x in args.ppl.split(",")]:
             Xi = [k / args.J for k in range(args.J)]
             try:
-                env = KSVecEnv(B, dict(N=args.N, L=args.L), Xi=Xi, precision=args.precision,
+                cfg = dict(N=args.N, L=args.L)
+                if args.dt is not None:
+                    cfg["dt"] = args.dt
+                if args.cfg_steps is not None:
+                    cfg["cfg_steps"] = args.cfg_steps
+                env = KSVecEnv(B, cfg, Xi=Xi, precision=args.precision, solver=args.solver,
                                reward_mode=args.reward_mode, points_per_lane=P)
             except Exception as exc:
                 print(json.dumps({"envs": B, "ppl": P, "error": str(exc)}))
@@ -59,10 +67,12 @@ def main():
             ms = t0.elapsed_time(t1) / K
             flops = 191.0 * args.N * env.cfg_steps * B
             info = env.launch_info()
-            print(json.dumps({"envs": B, "N": args.N, "precision": args.precision, "ppl": info["points_per_lane"],
+            print(json.dumps({"envs": B, "N": args.N, "solver": args.solver, "cfg_steps": env.cfg_steps, "dt": env.dt,
+                              "precision": args.precision, "ppl": info["points_per_lane"],
                               "lanes": info["lanes_per_env"], "regs": info["regs_per_thread"],
                               "grid": info["grid_blocks"], "ms_per_period": round(ms, 4),
-                              "periods_per_s": round(B / ms * 1e3), "tflops_alg": round(flops / ms / 1e9, 2),
+                              "periods_per_s": round(B / ms * 1e3),
+                              "us_per_substep": round(ms * 1e3 / env.cfg_steps, 4), "tflops_alg": round(flops / ms / 1e9, 2),
                               "nonfinite": bool(env.nonfinite().any())}), flush=True)
             env.close()
 
