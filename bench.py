@@ -232,7 +232,7 @@ def run_gpu_arm(args):
     import torch.distributed as dist
 
     from model_based_pde_control_b200 import KSVecEnv, _lib
-    from model_based_pde_control_b200.sharding import gather_packed
+    from model_based_pde_control_b200.sharding import connect_fused_gather, gather_packed
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -241,11 +241,15 @@ def run_gpu_arm(args):
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    json_out = sys.stdout
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # stdout carries exactly ONE JSON line: anything NCCL prints (e.g. its version banner when
-        # NCCL_DEBUG=VERSION/INFO) goes to stderr
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        # stdout carries exactly ONE JSON line.  NCCL's C code prints its version banner straight to
+        # file descriptor 1 when NCCL_DEBUG is set, so fd 1 is pointed at stderr for the whole run and
+        # the JSON line goes to a private duplicate of the original stdout.
+        sys.stdout.flush()
+        json_out = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=dev)
 
     B = args.envs_per_gpu
@@ -265,10 +269,15 @@ def run_gpu_arm(args):
     stream = torch.cuda.current_stream(dev)
 
     fields = env.packed_fields()
+    fused = world > 1 and args.gather == "fused"
+    if fused:
+        connect_fused_gather(env)     # CUDA-IPC handles exchanged once; afterwards no collective call per period
 
     def one_step(k):
+        if fused:
+            return env.step_gather(actions[k])   # kernel epilogue stores into every peer's buffer + handshake
         out = env.step_device(actions[k])
-        if world > 1:
+        if world > 1 and args.gather == "nccl":
             out = gather_packed(out["packed"], fields, B)
         return out
 
@@ -305,6 +314,8 @@ def run_gpu_arm(args):
         total_ms = float(t.item())
     clocks = sampler.stop() if rank == 0 else None
     flags_bad = bool(env.nonfinite().any())
+    if fused and env.gather_timed_out():
+        raise SystemExit("fused gather: a peer never signalled (handshake timed out)")
 
     # ---- e2e: the gym-facing host API, host buffers, copies inside the timed region ----
     acts_host = rng.uniform(-1, 1, (W + K, B, 1, J)).astype(np.float32)
@@ -371,7 +382,11 @@ def run_gpu_arm(args):
                         "random actions (BASELINE.json configs[1] per GPU)",
             "envs_per_gpu": B, "total_envs": total_envs, "N": N, "J": J, "cfg_steps": S,
             "l2": "flushed (256 MiB memset) between timed steps, outside the per-step event pairs",
-            "collective": "none (N=1)" if world == 1 else "one NCCL all-gather of the packed obs/reward/step/truncated/flags block per period, timed",
+            "collective": "none (N=1)" if world == 1 else (
+                "fused: the period kernel's epilogue stores the packed obs/reward/step/truncated/flags block into every "
+                "peer's gather buffer over NVLink (CUDA-IPC peer stores) + one-warp epoch handshake, timed"
+                if fused else ("one NCCL all-gather of the packed obs/reward/step/truncated/flags block per period, timed"
+                               if args.gather == "nccl" else "NONE (diagnostic run: every rank keeps its shard to itself)")),
             "layout": env.launch_info(),
         },
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": env.h2d_bytes_per_step,
@@ -413,7 +428,7 @@ def run_gpu_arm(args):
                                       "sample": "plain-C oracle (oracle/ks_oracle.c, -O2, pthreads), 64 envs x 4 periods"}
         except Exception as exc:   # the C oracle is optional context
             line["cpu_baseline_c"] = {"error": str(exc)}
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=json_out, flush=True)
     env.close()
     if world > 1:
         dist.barrier()
@@ -433,6 +448,8 @@ def main():
     ap.add_argument("--burnin", type=int, default=40, help="device burn-in periods before timing")
     ap.add_argument("--cpu-periods", type=int, default=20, help="control periods per host core for cpu_baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--gather", default="fused", choices=["fused", "nccl", "none"],
+                    help="N>1: how every rank gets the full batch each period (default: fused peer stores)")
     ap.add_argument("--no-spectral", action="store_true", help="skip the extra spectral-ETDRK4 leg")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -138,6 +138,27 @@ int ks_step_host(ks_handle *h, const float *actions_host, void *out_host, void *
 /* offsets[5] = byte offsets of {reward, obs, step, truncated, nonfinite}; *total = block bytes. */
 int ks_out_layout(const ks_handle *h, size_t offsets[5], size_t *total);
 
+/* Fused all-gather of the packed output block (ks_out_layout) across the ranks of a sharded run
+ * -- the exchange that lets every learner rank see the whole batch (the reference's counterpart is
+ * gym's AsyncVectorEnv collecting the sub-env results in the parent, mbrl.py:81-86; worker.py:60-66).
+ * Instead of a separate collective after the kernel, the period kernel's epilogue stores every
+ * output both locally and, with plain st.global over NVLink, into this rank's slot of every peer's
+ * gather buffer (CUDA-IPC mapped), followed by a one-warp epoch handshake.  One process per GPU:
+ *   1. every rank: ks_gather_init(h, world, rank, handle[64], &slot_bytes)   allocates its buffer
+ *   2. exchange the 64-byte handles by any means (e.g. torch.distributed.all_gather_object)
+ *   3. every rank: ks_gather_connect(h, all_handles = [world][64] in rank order)
+ *   4. per period: ks_step_gather(h, actions_dev, &gathered, stream); `gathered` is a device
+ *      pointer to [world][slot_bytes]: rank r's packed block at r*slot_bytes, valid (for work
+ *      enqueued on `stream`) until the SECOND next ks_step_gather (double-buffered).
+ * All ranks must call ks_step_gather the same number of times.  A peer that never signals makes
+ * the handshake give up after ~2 s; ks_gather_status then reports timed_out = 1. */
+#define KS_MAX_WORLD 16
+#define KS_IPC_HANDLE_BYTES 64
+int ks_gather_init(ks_handle *h, int32_t world, int32_t rank, void *ipc_handle_out, size_t *slot_bytes);
+int ks_gather_connect(ks_handle *h, const void *all_handles);
+int ks_step_gather(ks_handle *h, const float *actions, void **gathered, void *stream);
+int ks_gather_status(ks_handle *h, int32_t *timed_out, void *stream);
+
 /* Mirrors np.seterr(over="raise") (kuramoto.py:12): flags[b] != 0 once env b's state went
  * non-finite (sticky until ks_reset / ks_set_state).  Synchronises `stream`.  *any (nullable)
  * receives the OR of all flags; nonfinite_host (nullable) the [B] flags. */

@@ -17,6 +17,7 @@ KS_F64, KS_F32 = 0, 1
 KS_REWARD_L2, KS_REWARD_DISSIPATION = 0, 1
 KS_HOST, KS_DEVICE = 0, 1
 KS_SOLVER_FD_RK4, KS_SOLVER_ETDRK4 = 0, 1
+KS_MAX_WORLD, KS_IPC_HANDLE_BYTES = 16, 64
 KS_ERR_ARG, KS_ERR_UNSUPPORTED, KS_ERR_NO_DEVICE, KS_ERR_STATE = -1, -2, -3, -4
 
 PRECISIONS = {"f64": KS_F64, "fp64": KS_F64, "float64": KS_F64, "f32": KS_F32, "fp32": KS_F32, "float32": KS_F32}
@@ -69,6 +70,10 @@ EXPORTS = {
     "ks_get_config": (ctypes.c_int, [_vp, ctypes.POINTER(KsConfig)]),
     "ks_launch_info": (ctypes.c_int, [_vp] + [ctypes.POINTER(_i32)] * 5),
     "ks_launch_count": (ctypes.c_uint64, [_vp]),
+    "ks_gather_init": (ctypes.c_int, [_vp, _i32, _i32, _vp, ctypes.POINTER(ctypes.c_size_t)]),
+    "ks_gather_connect": (ctypes.c_int, [_vp, _vp]),
+    "ks_step_gather": (ctypes.c_int, [_vp, _vp, ctypes.POINTER(_vp), _vp]),
+    "ks_gather_status": (ctypes.c_int, [_vp, ctypes.POINTER(_i32), _vp]),
     "ks_bench_fp64_peak": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                           ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]),
 }

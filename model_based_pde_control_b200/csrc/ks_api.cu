@@ -57,6 +57,14 @@ struct ks_handle {
     double *scratch64 = nullptr;  // [B,N] f64 staging for set/get_state in F32 mode and host ICs
     uint8_t *mask = nullptr;      // [B] staging for host reset masks
     void *etd_tables = nullptr;   // [kEtdTables][N] T: ETDRK4 coefficient tables (spectral solver only)
+    // fused all-gather over NVLink peer memory (ks_gather_*)
+    int g_world = 0, g_rank = 0;
+    uint8_t *g_buf = nullptr;       // local: [2 parities][world][out_total] + flags [world] u32 (own cudaMalloc)
+    uint8_t *g_peer[KS_MAX_WORLD] = {nullptr};   // every rank's buffer as mapped into this process (own = g_buf)
+    bool g_connected = false;
+    uint32_t g_epoch = 0;
+    int32_t *g_timeout = nullptr;   // device flag set by the wait kernel when a peer never signalled
+    size_t g_slot = 0, g_flags_off = 0, g_total = 0;
     size_t out_off[5] = {0, 0, 0, 0, 0}, out_total = 0;
     uint64_t launches = 0;
     char err[256] = "";
@@ -279,11 +287,36 @@ __global__ void eval_rows(int M, int N, double dx, int reward_mode, const double
     }
 }
 
+// Completion handshake of the fused all-gather: one thread per peer.  Thread r publishes this
+// rank's epoch into peer r's flag word (a peer store, after a system-scope fence: the period
+// kernel that wrote the payload retired earlier on the same stream) and then waits until peer r's
+// epoch shows up in the local flag word.  Only the GPUs of DIFFERENT ranks ever wait on each other
+// here; the spin is bounded (~2 s of SM clocks) and reports through *timeout instead of hanging.
+__global__ void gather_signal_wait(uint32_t *const *peer_flags, volatile uint32_t *local_flags, int world, int rank,
+                                   uint32_t epoch, int32_t *timeout)
+{
+    const int r = threadIdx.x;
+    if (r >= world || r == rank) return;
+    __threadfence_system();
+    *reinterpret_cast<volatile uint32_t *>(peer_flags[r] + rank) = epoch;
+    const long long t0 = clock64();
+    while ((int32_t)(local_flags[r] - epoch) < 0) {
+        if (clock64() - t0 > 4000000000LL) {
+            atomicExch(timeout, 1);
+            break;
+        }
+        __nanosleep(64);
+    }
+    __threadfence_system();
+}
+
 int launch_period(ks_handle *h, int K, const float *actions, const float *phi, float *obs, double *reward,
                   uint8_t *truncated, int32_t *step, uint8_t *nonfinite_out, int reset_timestep, const uint8_t *mask,
-                  cudaStream_t stream)
+                  cudaStream_t stream, int n_remote = 0, const long long *remote_delta = nullptr)
 {
     ks::Params p;
+    p.n_remote = n_remote;
+    for (int q = 0; q < ks::kMaxRemote; ++q) p.remote_delta[q] = q < n_remote ? remote_delta[q] : 0;
     p.u = h->u;
     p.timestep = h->timestep;
     p.nonfinite = h->nonfinite;
@@ -472,6 +505,11 @@ int ks_destroy(ks_handle *h)
         cudaFree(h->scratch64);
         cudaFree(h->mask);
         cudaFree(h->etd_tables);
+        if (h->g_connected)
+            for (int r = 0; r < h->g_world; ++r)
+                if (r != h->g_rank && h->g_peer[r]) cudaIpcCloseMemHandle(h->g_peer[r]);
+        cudaFree(h->g_buf);
+        cudaFree(h->g_timeout);
         cudaGetLastError();
     }
     delete h;
@@ -662,6 +700,100 @@ int ks_eval(ks_handle *h, int32_t M, const double *u, const float *phi, double *
                                                         uxxxx, reward);
     KS_CUDA(h, cudaGetLastError());
     h->launches += 1;
+    return KS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Fused all-gather of the packed output block over NVLink peer memory
+// ---------------------------------------------------------------------------------------------
+int ks_gather_init(ks_handle *h, int32_t world, int32_t rank, void *ipc_handle_out, size_t *slot_bytes)
+{
+    if (!h || !ipc_handle_out) return h ? fail(h, KS_ERR_ARG, "ks_gather_init: NULL argument") : KS_ERR_ARG;
+    if (world < 1 || world > KS_MAX_WORLD || rank < 0 || rank >= world)
+        return fail(h, KS_ERR_ARG, "ks_gather_init: world=%d rank=%d (max world %d)", world, rank, KS_MAX_WORLD);
+    if (h->g_buf) return fail(h, KS_ERR_STATE, "ks_gather_init: already initialised");
+    static_assert(sizeof(cudaIpcMemHandle_t) == KS_IPC_HANDLE_BYTES, "IPC handle size");
+    DeviceGuard guard(h->cfg.device);
+    h->g_world = world;
+    h->g_rank = rank;
+    h->g_slot = (h->out_total + 255) & ~size_t(255);
+    h->g_flags_off = 2 * (size_t)world * h->g_slot;
+    h->g_total = h->g_flags_off + 256;
+    KS_CUDA(h, cudaMalloc(&h->g_buf, h->g_total));
+    KS_CUDA(h, cudaMemset(h->g_buf, 0, h->g_total));
+    KS_CUDA(h, cudaMalloc(&h->g_timeout, 2 * sizeof(int32_t) + KS_MAX_WORLD * sizeof(void *)));
+    KS_CUDA(h, cudaMemset(h->g_timeout, 0, 2 * sizeof(int32_t) + KS_MAX_WORLD * sizeof(void *)));
+    KS_CUDA(h, cudaDeviceSynchronize());
+    cudaIpcMemHandle_t hd;
+    KS_CUDA(h, cudaIpcGetMemHandle(&hd, h->g_buf));
+    memcpy(ipc_handle_out, &hd, sizeof(hd));
+    if (slot_bytes) *slot_bytes = h->g_slot;
+    h->g_peer[rank] = h->g_buf;
+    return KS_OK;
+}
+
+int ks_gather_connect(ks_handle *h, const void *all_handles)
+{
+    if (!h || !all_handles) return h ? fail(h, KS_ERR_ARG, "ks_gather_connect: NULL argument") : KS_ERR_ARG;
+    if (!h->g_buf) return fail(h, KS_ERR_STATE, "ks_gather_connect: call ks_gather_init first");
+    if (h->g_connected) return fail(h, KS_ERR_STATE, "ks_gather_connect: already connected");
+    DeviceGuard guard(h->cfg.device);
+    const uint8_t *hs = static_cast<const uint8_t *>(all_handles);
+    for (int r = 0; r < h->g_world; ++r) {
+        if (r == h->g_rank) continue;
+        cudaIpcMemHandle_t hd;
+        memcpy(&hd, hs + (size_t)r * KS_IPC_HANDLE_BYTES, sizeof(hd));
+        void *ptr = nullptr;
+        KS_CUDA(h, cudaIpcOpenMemHandle(&ptr, hd, cudaIpcMemLazyEnablePeerAccess));
+        h->g_peer[r] = static_cast<uint8_t *>(ptr);
+    }
+    // table of every rank's flag array for the signal kernel (lives behind the timeout word)
+    uint32_t *flags[KS_MAX_WORLD] = {nullptr};
+    for (int r = 0; r < h->g_world; ++r) flags[r] = reinterpret_cast<uint32_t *>(h->g_peer[r] + h->g_flags_off);
+    KS_CUDA(h, cudaMemcpy(h->g_timeout + 2, flags, sizeof(flags), cudaMemcpyHostToDevice));
+    h->g_connected = true;
+    return KS_OK;
+}
+
+int ks_step_gather(ks_handle *h, const float *actions, void **gathered, void *stream_)
+{
+    if (!h || !actions) return h ? fail(h, KS_ERR_ARG, "ks_step_gather: NULL argument") : KS_ERR_ARG;
+    if (!h->g_buf || (h->g_world > 1 && !h->g_connected))
+        return fail(h, KS_ERR_STATE, "ks_step_gather: gather not initialised / connected");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    DeviceGuard guard(h->cfg.device);
+    h->g_epoch += 1;
+    const size_t parity_off = (size_t)(h->g_epoch & 1u) * h->g_world * h->g_slot;
+    uint8_t *mine = h->g_buf + parity_off + (size_t)h->g_rank * h->g_slot;
+    long long delta[ks::kMaxRemote];
+    int n = 0;
+    for (int r = 0; r < h->g_world; ++r) {
+        if (r == h->g_rank) continue;
+        uint8_t *theirs = h->g_peer[r] + parity_off + (size_t)h->g_rank * h->g_slot;
+        delta[n++] = (long long)(theirs - mine);
+    }
+    int rc = launch_period(h, 1, actions, nullptr, (float *)(mine + h->out_off[1]), (double *)(mine + h->out_off[0]),
+                           mine + h->out_off[3], (int32_t *)(mine + h->out_off[2]), mine + h->out_off[4], 0, nullptr, stream,
+                           n, delta);
+    if (rc != KS_OK) return rc;
+    if (h->g_world > 1) {
+        gather_signal_wait<<<1, 32, 0, stream>>>(reinterpret_cast<uint32_t *const *>(h->g_timeout + 2),
+                                                 reinterpret_cast<volatile uint32_t *>(h->g_buf + h->g_flags_off), h->g_world,
+                                                 h->g_rank, h->g_epoch, h->g_timeout);
+        KS_CUDA(h, cudaGetLastError());
+        h->launches += 1;
+    }
+    if (gathered) *gathered = h->g_buf + parity_off;
+    return KS_OK;
+}
+
+int ks_gather_status(ks_handle *h, int32_t *timed_out, void *stream_)
+{
+    if (!h || !timed_out) return KS_ERR_ARG;
+    if (!h->g_timeout) return fail(h, KS_ERR_STATE, "ks_gather_status: gather not initialised");
+    DeviceGuard guard(h->cfg.device);
+    KS_CUDA(h, cudaMemcpyAsync(timed_out, h->g_timeout, sizeof(int32_t), cudaMemcpyDeviceToHost, (cudaStream_t)stream_));
+    KS_CUDA(h, cudaStreamSynchronize((cudaStream_t)stream_));
     return KS_OK;
 }
 

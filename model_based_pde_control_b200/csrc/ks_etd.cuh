@@ -388,37 +388,58 @@ __global__ void __launch_bounds__(kBlockThreads) ks_etd_kernel(const EtdParams e
                     if (actA) oa[8 * r] = (float)ux[r];
                     if (actB) ob[8 * r] = (float)uy[r];
                 }
+                for (int q = 0; q < p.n_remote; ++q) {
+                    float *ra_ = remote_ptr(oa, p.remote_delta[q]), *rb_ = remote_ptr(ob, p.remote_delta[q]);
+#pragma unroll
+                    for (int r = 0; r < 8; ++r) {
+                        if (actA) ra_[8 * r] = (float)ux[r];
+                        if (actB) rb_[8 * r] = (float)uy[r];
+                    }
+                }
             } else {
                 const int first = p.obs_stride / 2;
 #pragma unroll
                 for (int r = 0; r < 8; ++r) {
                     const int idx = l + 8 * r - first;
                     if (idx >= 0 && idx % p.obs_stride == 0) {
-                        if (actA) p.obs[((size_t)k * p.B + envA) * p.obs_len + idx / p.obs_stride] = (float)ux[r];
-                        if (actB) p.obs[((size_t)k * p.B + envB) * p.obs_len + idx / p.obs_stride] = (float)uy[r];
+                        float *da = p.obs + ((size_t)k * p.B + envA) * p.obs_len + idx / p.obs_stride;
+                        float *db = p.obs + ((size_t)k * p.B + envB) * p.obs_len + idx / p.obs_stride;
+                        if (actA) *da = (float)ux[r];
+                        if (actB) *db = (float)uy[r];
+                        for (int q = 0; q < p.n_remote; ++q) {
+                            if (actA) *remote_ptr(da, p.remote_delta[q]) = (float)ux[r];
+                            if (actB) *remote_ptr(db, p.remote_delta[q]) = (float)uy[r];
+                        }
                     }
                 }
             }
         }
         if (l == 0) {
-            if (actA) {
-                const size_t kb = (size_t)k * p.B + envA;
-                if (p.reward != nullptr) p.reward[kb] = -(ra * p.inv_N) * p.inv_cfg_steps;
-                if (p.truncated != nullptr) p.truncated[kb] = tsA >= p.max_episode_steps ? 1 : 0;
-                if (p.step != nullptr) p.step[kb] = tsA;
-                if (anyA) { badA = true; p.nonfinite[envA] = 1; }
-                if (p.nonfinite_out != nullptr) p.nonfinite_out[kb] = badA ? 1 : 0;
-            }
-            if (actB) {
-                const size_t kb = (size_t)k * p.B + envB;
-                if (p.reward != nullptr) p.reward[kb] = -(rb * p.inv_N) * p.inv_cfg_steps;
-                if (p.truncated != nullptr) p.truncated[kb] = tsB >= p.max_episode_steps ? 1 : 0;
-                if (p.step != nullptr) p.step[kb] = tsB;
-                if (anyB) { badB = true; p.nonfinite[envB] = 1; }
-                if (p.nonfinite_out != nullptr) p.nonfinite_out[kb] = badB ? 1 : 0;
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const bool act = e ? actB : actA;
+                if (!act) continue;
+                const int env = e ? envB : envA, ts = e ? tsB : tsA;
+                bool &bad = e ? badB : badA;
+                if (e ? anyB : anyA) { bad = true; p.nonfinite[env] = 1; }
+                const size_t kb = (size_t)k * p.B + env;
+                const double rv = -((e ? rb : ra) * p.inv_N) * p.inv_cfg_steps;
+                const uint8_t tv = ts >= p.max_episode_steps ? 1 : 0, bv = bad ? 1 : 0;
+                if (p.reward != nullptr) p.reward[kb] = rv;
+                if (p.truncated != nullptr) p.truncated[kb] = tv;
+                if (p.step != nullptr) p.step[kb] = ts;
+                if (p.nonfinite_out != nullptr) p.nonfinite_out[kb] = bv;
+                for (int q = 0; q < p.n_remote; ++q) {     // gather mode: all four outputs are present
+                    const long long d = p.remote_delta[q];
+                    *remote_ptr(p.reward + kb, d) = rv;
+                    *remote_ptr(p.truncated + kb, d) = tv;
+                    *remote_ptr(p.step + kb, d) = ts;
+                    *remote_ptr(p.nonfinite_out + kb, d) = bv;
+                }
             }
         }
     }
+    if (p.n_remote > 0) __threadfence_system();   // peer stores performed before the launch retires
 
 #pragma unroll
     for (int r = 0; r < 8; ++r) {

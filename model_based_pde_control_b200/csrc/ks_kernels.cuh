@@ -25,6 +25,7 @@ namespace ks {
 constexpr int kBlockThreads = 128;
 constexpr int kHalo = 4;
 constexpr unsigned kFullMask = 0xffffffffu;
+constexpr int kMaxRemote = 15;   // peers a launch can mirror its outputs to (world size <= 16)
 
 enum { kRewardL2 = 0, kRewardDissipation = 1 };
 
@@ -57,7 +58,18 @@ struct Params {
     int obs_stride;        // SensorTransform stride s: obs = u[s/2::s] (transforms.py:236-239); 1 = all
     int obs_len;           // observation length, ceil((N - s/2) / s)
     double inv_cfg_steps, inv_N;
+    // Fused all-gather (ks_step_gather): every output store of the period epilogue is repeated at
+    // `pointer + remote_delta[q]`, q < n_remote -- this rank's slot in peer q's gather buffer, mapped
+    // into this process with CUDA IPC, i.e. plain st.global over NVLink.  n_remote = 0 otherwise.
+    int n_remote;
+    long long remote_delta[kMaxRemote];
 };
+
+template <typename U>
+__device__ __forceinline__ U *remote_ptr(U *local, long long delta)
+{
+    return reinterpret_cast<U *>(reinterpret_cast<char *>(local) + delta);
+}
 
 // ---------------------------------------------------------------------------------------------
 // small helpers
@@ -377,29 +389,45 @@ __global__ void __launch_bounds__(kBlockThreads) ks_period_kernel(const Params p
                     float o[P];
 #pragma unroll
                     for (int i = 0; i < P; ++i) o[i] = (float)u[i];
-                    store_row<P>(p.obs + (size_t)k * p.B * p.N + off, o);
+                    float *dst = p.obs + (size_t)k * p.B * p.N + off;
+                    store_row<P>(dst, o);
+                    for (int q = 0; q < p.n_remote; ++q) store_row<P>(remote_ptr(dst, p.remote_delta[q]), o);
                 } else {
                     float *orow = p.obs + ((size_t)k * p.B + env) * p.obs_len;
                     const int first = p.obs_stride / 2;
 #pragma unroll
                     for (int i = 0; i < P; ++i) {
                         const int idx = l * P + i - first;
-                        if (idx >= 0 && idx % p.obs_stride == 0) orow[idx / p.obs_stride] = (float)u[i];
+                        if (idx >= 0 && idx % p.obs_stride == 0) {
+                            orow[idx / p.obs_stride] = (float)u[i];
+                            for (int q = 0; q < p.n_remote; ++q)
+                                *remote_ptr(orow + idx / p.obs_stride, p.remote_delta[q]) = (float)u[i];
+                        }
                     }
                 }
             }
             if (l == 0) {
-                if (p.reward != nullptr) p.reward[kb] = -(tot * p.inv_N) * p.inv_cfg_steps;
-                if (p.truncated != nullptr) p.truncated[kb] = ts >= p.max_episode_steps ? 1 : 0;
-                if (p.step != nullptr) p.step[kb] = ts;
                 if (badmask & grp) {
                     was_bad = true;
                     p.nonfinite[env] = 1;
                 }
-                if (p.nonfinite_out != nullptr) p.nonfinite_out[kb] = was_bad ? 1 : 0;
+                const double rv = -(tot * p.inv_N) * p.inv_cfg_steps;
+                const uint8_t tv = ts >= p.max_episode_steps ? 1 : 0, bv = was_bad ? 1 : 0;
+                if (p.reward != nullptr) p.reward[kb] = rv;
+                if (p.truncated != nullptr) p.truncated[kb] = tv;
+                if (p.step != nullptr) p.step[kb] = ts;
+                if (p.nonfinite_out != nullptr) p.nonfinite_out[kb] = bv;
+                for (int q = 0; q < p.n_remote; ++q) {     // gather mode: all four outputs are present
+                    const long long d = p.remote_delta[q];
+                    *remote_ptr(p.reward + kb, d) = rv;
+                    *remote_ptr(p.truncated + kb, d) = tv;
+                    *remote_ptr(p.step + kb, d) = ts;
+                    *remote_ptr(p.nonfinite_out + kb, d) = bv;
+                }
             }
         }
     }
+    if (p.n_remote > 0) __threadfence_system();   // peer stores performed before the launch retires
 
     if (active) {
         store_row<P>(ug, u);

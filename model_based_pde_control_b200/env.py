@@ -168,6 +168,7 @@ class KSVecEnv(VectorEnvBase):
         self._h_act = self._act_pinned.numpy()
         # device-side outputs of the tensor API (allocated on first use)
         self._d_out = None
+        self._gather = None
         self._pending_actions = None
         self.h2d_bytes_per_step = B * self.J * 4
         self.d2h_bytes_per_step = int(total.value)
@@ -420,6 +421,62 @@ class KSVecEnv(VectorEnvBase):
                                               _ptr(out["truncated"]), _ptr(out["step"]), _ptr(out["nonfinite"]),
                                               self._stream()))
         return out
+
+    # ------------------------------------------------------------------ fused all-gather (multi-GPU)
+    def gather_init(self, world: int, rank: int) -> bytes:
+        """Allocate this rank's gather buffer (``ks_gather_init``); returns the 64-byte CUDA-IPC
+        handle that the other ranks need (exchange it with any host-side collective)."""
+        self._check_open()
+        handle = ctypes.create_string_buffer(_lib.KS_IPC_HANDLE_BYTES)
+        slot = ctypes.c_size_t()
+        _lib.check(self._h, self._lib.ks_gather_init(self._h, world, rank, handle, ctypes.byref(slot)))
+        self._gather = dict(world=world, rank=rank, slot=int(slot.value), views={})
+        return handle.raw
+
+    def gather_connect(self, handles: Sequence[bytes]) -> None:
+        """Map every peer's gather buffer into this process (``ks_gather_connect``); ``handles`` in rank order."""
+        self._check_open()
+        blob = b"".join(bytes(h) for h in handles)
+        if len(blob) != self._gather["world"] * _lib.KS_IPC_HANDLE_BYTES:
+            raise ValueError("need one 64-byte IPC handle per rank, in rank order")
+        _lib.check(self._h, self._lib.ks_gather_connect(self._h, blob))
+
+    def step_gather(self, actions: torch.Tensor) -> dict:
+        """One control period of the local shard whose kernel epilogue also stores the outputs into
+        every peer's gather buffer over NVLink (``ks_step_gather``).  Returns full-batch views
+        ``{name: [world, local_envs, ...]}`` (rank order = env order) into the double-buffered gather
+        block: valid until the second next call.  Stream-ordered, no host synchronisation."""
+        self._check_open()
+        if self._gather is None:
+            raise RuntimeError("step_gather() before gather_init() / gather_connect()")
+        a = actions.to(device=self.device, dtype=torch.float32).reshape(self.num_envs, self.J).contiguous()
+        ptr = ctypes.c_void_p()
+        _lib.check(self._h, self._lib.ks_step_gather(self._h, _ptr(a), ctypes.byref(ptr), self._stream()))
+        g = self._gather
+        views = g["views"].get(ptr.value)
+        if views is None:
+            world, slot, B = g["world"], g["slot"], self.num_envs
+
+            class _Raw:     # zero-copy torch view of library-owned device memory
+                __cuda_array_interface__ = {"shape": (world * slot,), "typestr": "|u1", "data": (ptr.value, False),
+                                            "version": 3, "strides": None}
+
+            rows = torch.as_tensor(_Raw(), device=self.device).view(world, slot)
+            views = {"packed": rows}
+            for name, (off, dtype, shape) in self.packed_fields().items():
+                n = B
+                for d in shape:
+                    n *= d
+                nbytes = n * torch.empty((), dtype=dtype).element_size()
+                views[name] = rows[:, off:off + nbytes].view(dtype).reshape((world, B) + tuple(shape))
+            g["views"][ptr.value] = views
+        return views
+
+    def gather_timed_out(self) -> bool:
+        """True once a peer failed to signal within the handshake's bound (synchronises the stream)."""
+        flag = ctypes.c_int32()
+        _lib.check(self._h, self._lib.ks_gather_status(self._h, ctypes.byref(flag), self._stream()))
+        return bool(flag.value)
 
     def rollout_device(self, actions: Optional[torch.Tensor], K: Optional[int] = None, outputs: bool = True) -> dict:
         """``K`` control periods in ONE persistent launch (open loop).  ``actions``: CUDA float32

@@ -74,6 +74,21 @@ def gather_packed(packed_local: torch.Tensor, fields: dict, local_envs: int, gro
     return out
 
 
+def connect_fused_gather(env, group=None) -> None:
+    """Set up the fused all-gather of ``env`` (a local ``KSVecEnv`` shard) across ``group``: every
+    rank allocates its gather buffer, the 64-byte CUDA-IPC handles travel through one host-side
+    ``all_gather_object``, every rank maps its peers' buffers.  Equal shards only (checked)."""
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    handle = env.gather_init(world, rank)
+    infos = [None] * world
+    dist.all_gather_object(infos, (env.num_envs, handle), group=group)
+    if len({n for n, _ in infos}) != 1:
+        raise ValueError(f"fused gather needs equal shards, got {[n for n, _ in infos]}")
+    env.gather_connect([h for _, h in infos])
+    dist.barrier(group)      # nobody launches a peer-writing kernel before everyone is mapped
+
+
 class ShardedKSVecEnv:
     """``num_envs`` environments spread over the ranks of a ``torch.distributed`` group.
 
@@ -97,6 +112,7 @@ class ShardedKSVecEnv:
 
             env_factory = lambda n: KSVecEnv(n, config, **kwargs)  # noqa: E731
         self.local = env_factory(self.hi - self.lo)
+        self._fused = False
 
     @property
     def local_num_envs(self) -> int:
@@ -114,7 +130,15 @@ class ShardedKSVecEnv:
     def step_device(self, actions: torch.Tensor, gather: bool = True) -> dict:
         """Step the local shard with this rank's rows of the full action batch.  ``gather=True``
         returns full-batch tensors ``[num_envs, ...]``; ``gather="packed"`` uses the single-
-        collective path and returns ``[world, local_envs, ...]`` views (equal shards)."""
+        collective path and returns ``[world, local_envs, ...]`` views (equal shards);
+        ``gather="fused"`` returns the same views filled by the kernel epilogues themselves
+        (peer stores over NVLink + epoch handshake, ``ks_step_gather``) -- no NCCL call per period."""
+        if gather == "fused" and self.world_size > 1:
+            # kernel epilogue stores straight into every peer's buffer over NVLink (no collective call)
+            if not self._fused:
+                connect_fused_gather(self.local, self.group)
+                self._fused = True
+            return self.local.step_gather(self.local_slice(actions.reshape(self.num_envs, -1)))
         out = self.local.step_device(self.local_slice(actions.reshape(self.num_envs, -1)))
         if not gather:
             return out

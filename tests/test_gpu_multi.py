@@ -1,0 +1,118 @@
+"""Multi-GPU checks (need >= 2 B200s on one box: ``gpurun --gpus 2 -- python -m pytest tests/test_gpu_multi.py -m gpu``;
+skipped on a 1-GPU box).  Each test launches ``torchrun`` with one rank per GPU.
+
+* fused all-gather (``ks_step_gather``: the period kernel's epilogue stores into every peer's buffer
+  over NVLink + epoch handshake) == the NCCL all-gather of the packed block, bit for bit, over many
+  consecutive periods (double-buffer / handshake hazards would show as stale rows);
+* sharded trajectories == the single-GPU trajectory of the same envs, bit for bit.
+"""
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+WORKER = r'''
+import os, sys
+sys.path.insert(0, os.environ["KS_ROOT"])
+import numpy as np, torch, torch.distributed as dist
+from model_based_pde_control_b200 import KSVecEnv
+from model_based_pde_control_b200.sharding import connect_fused_gather, gather_packed, shard_range
+
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dev = torch.device("cuda", local)
+dist.init_process_group("nccl", device_id=dev)
+solver = os.environ.get("KS_SOLVER", "fd_rk4")
+cfg = dict(dt=0.025, cfg_steps=10) if solver == "etdrk4" else dict(cfg_steps=25)
+B_total, K = 1024, 12
+lo, hi = shard_range(B_total, rank, world)
+rng = np.random.default_rng(0)
+u0 = rng.uniform(-1, 1, (B_total, 64))
+acts = torch.as_tensor(rng.uniform(-1, 1, (K, B_total, 4)).astype(np.float32)).to(dev)
+
+env = KSVecEnv(hi - lo, cfg, device=local, solver=solver)          # fused path
+ref = KSVecEnv(hi - lo, cfg, device=local, solver=solver)          # NCCL path
+env.set_state(u0[lo:hi], 0); ref.set_state(u0[lo:hi], 0)
+connect_fused_gather(env)
+fields = ref.packed_fields()
+ok = True
+for k in range(K):
+    g = env.step_gather(acts[k, lo:hi])
+    o = ref.step_device(acts[k, lo:hi])
+    n = gather_packed(o["packed"], fields, hi - lo)
+    for name in ("obs", "reward", "step", "truncated", "nonfinite"):
+        ok = ok and torch.equal(g[name], n[name])
+    ok = ok and int(g["step"].min()) == k + 1 == int(g["step"].max())
+assert not env.gather_timed_out()
+
+# the gathered batch equals the single-GPU run of all envs (rank 0 computes it)
+if rank == 0:
+    full = KSVecEnv(B_total, cfg, device=local, solver=solver)
+    full.set_state(u0, 0)
+    for k in range(K):
+        f = full.step_device(acts[k])
+    ok = ok and torch.equal(f["obs"], g["obs"].reshape(B_total, -1)) and torch.equal(f["reward"], g["reward"].reshape(-1))
+    full.close()
+t = torch.tensor([1 if ok else 0], device=dev)
+dist.all_reduce(t, op=dist.ReduceOp.MIN)
+if rank == 0:
+    print("MULTI_GPU_OK" if int(t.item()) == 1 else "MULTI_GPU_MISMATCH", flush=True)
+env.close(); ref.close()
+dist.barrier(); dist.destroy_process_group()
+'''
+
+
+def _run(world, solver):
+    import torch
+
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs, have {torch.cuda.device_count()}")
+    env = dict(os.environ, KS_ROOT=ROOT, KS_SOLVER=solver)
+    path = os.path.join(ROOT, "gpurun_out", f"_multi_worker_{solver}.py")     # torchrun needs a script file
+    os.makedirs(os.path.dirname(path), exist_ok=True)
+    with open(path, "w") as f:
+        f.write(WORKER)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+           "--master-addr", "127.0.0.1", "--master-port", "29611", path]
+    res = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-4000:]
+    assert "MULTI_GPU_OK" in res.stdout, res.stdout[-2000:] + res.stderr[-2000:]
+
+
+@pytest.mark.parametrize("solver", ["fd_rk4", "etdrk4"])
+def test_fused_gather_equals_nccl_gather_and_single_gpu_2gpus(solver):
+    _run(2, solver)
+
+
+def test_fused_gather_4gpus():
+    _run(4, "fd_rk4")
+
+
+def test_fused_gather_world1_equals_step_device():
+    """World size 1 (runs on any GPU box): the gather path with no peers is the plain step."""
+    import numpy as np
+    import torch
+
+    from model_based_pde_control_b200 import KSVecEnv
+
+    B = 37
+    rng = np.random.default_rng(1)
+    u0 = rng.uniform(-1, 1, (B, 64))
+    a = torch.as_tensor(rng.uniform(-1, 1, (3, B, 4)).astype(np.float32)).cuda()
+    e1, e2 = KSVecEnv(B, cfg_steps=20), KSVecEnv(B, cfg_steps=20)
+    e1.set_state(u0, 0); e2.set_state(u0, 0)
+    h = e1.gather_init(1, 0)
+    assert len(h) == 64
+    e1.gather_connect([h])
+    for k in range(3):
+        g = e1.step_gather(a[k])
+        o = e2.step_device(a[k])
+        for name in ("obs", "reward", "step", "truncated", "nonfinite"):
+            assert g[name].shape[0] == 1 and torch.equal(g[name][0], o[name])
+    assert not e1.gather_timed_out()
+    e1.close(); e2.close()

@@ -99,3 +99,52 @@ def test_single_process_passthrough():
     assert (env.rank, env.world_size, env.lo, env.hi) == (0, 1, 0, 6)
     out = env.step_device(torch.arange(6.0)[:, None].repeat(1, 4))
     assert out["reward"].tolist() == [-0.0, -1.0, -2.0, -3.0, -4.0, -5.0]
+
+
+# ---- fused-gather orchestration (host side): handle exchange in rank order, equal-shard check --------------
+class StubGatherEnv(StubEnv):
+    """Records what the host-side set-up of the fused gather hands to the C ABI (the peer stores
+    themselves need NVLink; tests/test_gpu_multi.py covers them on 2 GPUs)."""
+
+    def gather_init(self, world, rank):
+        self.world, self.rank = world, rank
+        return bytes([rank]) * 64                     # a 64-byte "IPC handle" that names its owner
+
+    def gather_connect(self, handles):
+        self.handles = [bytes(h) for h in handles]
+
+    def step_gather(self, actions):
+        return {"rows": actions.shape[0], "handles": self.handles}
+
+
+def _fused_worker(rank, world, port, num_envs, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        env = ShardedKSVecEnv(num_envs, env_factory=lambda n: StubGatherEnv(n))
+        actions = torch.zeros(num_envs, 4)
+        try:
+            out = env.step_device(actions, gather="fused")
+            ok = (env.local.world, env.local.rank) == (world, rank) and out["rows"] == env.local_num_envs
+            ok = ok and out["handles"] == [bytes([r]) * 64 for r in range(world)]
+            env.step_device(actions, gather="fused")      # connects only once
+            q.put((rank, bool(ok)))
+        except ValueError as exc:                          # ragged shards are refused on every rank
+            q.put((rank, "equal shards" in str(exc)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,num_envs", [(2, 16), (3, 12), (3, 10)])
+def test_fused_gather_setup(world, num_envs):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_fused_worker, args=(r, world, port, num_envs, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    results = dict(q.get(timeout=5) for _ in range(world))
+    assert results == {r: True for r in range(world)}
