@@ -296,8 +296,14 @@ def run_gpu_arm(args):
         dist.barrier()
     torch.cuda.synchronize(dev)
     wall0 = time.perf_counter()
+    align = torch.zeros(1, device=dev)
     for k in range(K):
         flush.zero_()                      # L2 flush between timed steps (outside the event pair)
+        if world > 1:
+            # the 256 MiB memsets do not take equally long on every GPU; re-align the ranks on the
+            # device (stream-ordered 4-byte all-reduce, outside the event pair) so that a timed step
+            # is the period + exchange, not the previous flush's skew
+            dist.all_reduce(align)
         starts[k].record(stream)
         one_step(W + k)
         stops[k].record(stream)
@@ -381,7 +387,8 @@ def run_gpu_arm(args):
                         f"cfg_steps={S} RK4 sub-steps per control period, dt={env.dt}, {args.precision}, "
                         "random actions (BASELINE.json configs[1] per GPU)",
             "envs_per_gpu": B, "total_envs": total_envs, "N": N, "J": J, "cfg_steps": S,
-            "l2": "flushed (256 MiB memset) between timed steps, outside the per-step event pairs",
+            "l2": "flushed (256 MiB memset) between timed steps, outside the per-step event pairs"
+                  + ("; ranks re-aligned after each flush by a 4-byte all-reduce, also outside the pairs" if world > 1 else ""),
             "collective": "none (N=1)" if world == 1 else (
                 "fused: the period kernel's epilogue stores the packed obs/reward/step/truncated/flags block into every "
                 "peer's gather buffer over NVLink (CUDA-IPC peer stores) + one-warp epoch handshake, timed"

@@ -388,13 +388,27 @@ __global__ void __launch_bounds__(kBlockThreads) ks_etd_kernel(const EtdParams e
                     if (actA) oa[8 * r] = (float)ux[r];
                     if (actB) ob[8 * r] = (float)uy[r];
                 }
-                for (int q = 0; q < p.n_remote; ++q) {
-                    float *ra_ = remote_ptr(oa, p.remote_delta[q]), *rb_ = remote_ptr(ob, p.remote_delta[q]);
+                if (p.n_remote > 0) {
+                    // gather mode: stage the warp's 8 rows (512 floats, contiguous in the batch) in the
+                    // transpose tile and mirror them to the peers as coalesced 16-byte-per-lane stores
+                    float *stg = reinterpret_cast<float *>(&s_tile[wib][0]);
+                    __syncwarp();
 #pragma unroll
                     for (int r = 0; r < 8; ++r) {
-                        if (actA) ra_[8 * r] = (float)ux[r];
-                        if (actB) rb_[8 * r] = (float)uy[r];
+                        stg[(2 * grp) * N + l + 8 * r] = (float)ux[r];
+                        stg[(2 * grp + 1) * N + l + 8 * r] = (float)uy[r];
                     }
+                    __syncwarp();
+                    float *wbase = p.obs + ((size_t)k * p.B + (size_t)warp * 8) * N;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int i4 = j * 32 + lane, e = warp * 8 + (i4 * 4) / N;     // env that owns this float4
+                        if (e >= p.B || (p.mask != nullptr && p.mask[e] == 0)) continue;
+                        const float4 v = *reinterpret_cast<const float4 *>(stg + i4 * 4);
+                        for (int q = 0; q < p.n_remote; ++q)
+                            *reinterpret_cast<float4 *>(remote_ptr(wbase + i4 * 4, p.remote_delta[q])) = v;
+                    }
+                    __syncwarp();
                 }
             } else {
                 const int first = p.obs_stride / 2;

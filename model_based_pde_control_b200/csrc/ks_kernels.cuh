@@ -307,6 +307,10 @@ __device__ __forceinline__ void rk4_stage(T (&u)[P], T (&us)[P], T (&acc)[P], co
 template <typename T, int P, int RMODE>
 __global__ void __launch_bounds__(kBlockThreads) ks_period_kernel(const Params p, const Coef<T> c)
 {
+    // gather mode only: the warp's observation rows are staged here so that the stores into the
+    // peers' buffers leave as fully coalesced 16-byte-per-lane runs (NVLink packets of 128 B+
+    // instead of scattered 16 B pieces)
+    __shared__ __align__(16) float s_obs[kBlockThreads / 32][32 * P];
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * kBlockThreads + threadIdx.x) >> 5;
     if (warp * p.envs_per_warp >= p.B) return;  // warp-uniform
@@ -389,9 +393,8 @@ __global__ void __launch_bounds__(kBlockThreads) ks_period_kernel(const Params p
                     float o[P];
 #pragma unroll
                     for (int i = 0; i < P; ++i) o[i] = (float)u[i];
-                    float *dst = p.obs + (size_t)k * p.B * p.N + off;
-                    store_row<P>(dst, o);
-                    for (int q = 0; q < p.n_remote; ++q) store_row<P>(remote_ptr(dst, p.remote_delta[q]), o);
+                    if (p.n_remote == 0) store_row<P>(p.obs + (size_t)k * p.B * p.N + off, o);
+                    else store_row<P>(s_obs[threadIdx.x >> 5] + lane * P, o);     // staged, written out below
                 } else {
                     float *orow = p.obs + ((size_t)k * p.B + env) * p.obs_len;
                     const int first = p.obs_stride / 2;
@@ -425,6 +428,31 @@ __global__ void __launch_bounds__(kBlockThreads) ks_period_kernel(const Params p
                     *remote_ptr(p.nonfinite_out + kb, d) = bv;
                 }
             }
+        }
+        if (p.n_remote > 0 && p.obs != nullptr && p.obs_stride <= 1) {
+            // coalesced write-out of the staged rows: local copy + every peer's copy
+            const unsigned actmask = __ballot_sync(kFullMask, active);
+            __syncwarp();
+            float *wbase = p.obs + ((size_t)k * p.B + (size_t)warp * p.envs_per_warp) * p.N;
+            const float *srow = s_obs[threadIdx.x >> 5];
+            const int nfl = p.envs_per_warp * p.N;              // floats of this warp's rows
+            if constexpr (P % 4 == 0) {
+                for (int i4 = lane; i4 * 4 < nfl; i4 += 32) {
+                    if (!((actmask >> ((i4 * 4) / P)) & 1u)) continue;
+                    const float4 v = *reinterpret_cast<const float4 *>(srow + i4 * 4);
+                    *reinterpret_cast<float4 *>(wbase + i4 * 4) = v;
+                    for (int q = 0; q < p.n_remote; ++q)
+                        *reinterpret_cast<float4 *>(remote_ptr(wbase + i4 * 4, p.remote_delta[q])) = v;
+                }
+            } else {
+                for (int i = lane; i < nfl; i += 32) {
+                    if (!((actmask >> (i / P)) & 1u)) continue;
+                    const float v = srow[i];
+                    wbase[i] = v;
+                    for (int q = 0; q < p.n_remote; ++q) *remote_ptr(wbase + i, p.remote_delta[q]) = v;
+                }
+            }
+            __syncwarp();
         }
     }
     if (p.n_remote > 0) __threadfence_system();   // peer stores performed before the launch retires
