@@ -62,9 +62,14 @@ def test_spectrum_and_dissipation_within_one_percent(name, B):
     big = ref > 0.01 * ref.sum()                     # wavenumbers holding more than 1 % of the energy
     assert big.sum() >= 3
     rel = np.abs(spec[big] - ref[big]) / ref[big]
+    # per bin: 1 %, widened to 4 standard errors of the REFERENCE statistic where the fixture's own
+    # sampling error is larger than that (stats_large: 1024 reference episodes -> ~1 % per bin)
+    tol = np.maximum(TOL, 4.0 * g["spectrum_sem"][big] / ref[big])
     print(f"{name}: spectrum rel. dev (bins {np.nonzero(big)[0].tolist()}): {np.round(rel, 4).tolist()}; "
           f"dissipation {diss:.5f} vs {float(g['dissipation']):.5f}; mean u^2 {u2:.5f} vs {float(g['mean_u2']):.5f}")
-    assert rel.max() <= TOL
+    assert (rel <= tol).all(), (rel / tol).max()
+    # the energy in those bins taken together (sampling error averages out): strictly 1 %
+    assert abs(spec[big].sum() / ref[big].sum() - 1) <= TOL
     assert abs(diss - float(g["dissipation"])) <= TOL * abs(float(g["dissipation"]))
     assert abs(u2 - float(g["mean_u2"])) <= TOL * float(g["mean_u2"])
     assert abs(rew - float(g["mean_reward"])) <= TOL * abs(float(g["mean_reward"]))
