@@ -20,6 +20,7 @@ from __future__ import annotations
 import ctypes
 import math
 import os
+import sys
 from typing import Optional, Sequence
 
 import numpy as np
@@ -157,13 +158,9 @@ class KSVecEnv(VectorEnvBase):
         _lib.check(self._h, lib.ks_out_layout(self._h, ctypes.byref(offs), ctypes.byref(total)))
         B, N = num_envs, self.N
         self._out_offsets = [int(x) for x in offs]
-        self._out_pinned = torch.empty(total.value, dtype=torch.uint8, pin_memory=True)
-        host = self._out_pinned.numpy()
-        self._h_reward = host[offs[0]:offs[0] + 8 * B].view(np.float64)
-        self._h_obs = host[offs[1]:offs[1] + 4 * B * self.obs_len].view(np.float32).reshape(B, 1, self.obs_len)
-        self._h_step = host[offs[2]:offs[2] + 4 * B].view(np.int32)
-        self._h_trunc = host[offs[3]:offs[3] + B].view(np.uint8)
-        self._h_bad = host[offs[4]:offs[4] + B].view(np.uint8)
+        self._out_total = int(total.value)
+        self._blocks = [self._new_block()]          # pinned result blocks (see _free_block)
+        self._out_pinned = self._blocks[0]["pinned"]
         self._act_pinned = torch.empty((B, self.J), dtype=torch.float32, pin_memory=True)
         self._h_act = self._act_pinned.numpy()
         # device-side outputs of the tensor API (allocated on first use)
@@ -326,17 +323,22 @@ class KSVecEnv(VectorEnvBase):
         if not self._pending_actions:
             raise RuntimeError("step_wait() called without step_async()")
         self._pending_actions = None
-        _lib.check(self._h, self._lib.ks_step_host(self._h, self._h_act.ctypes.data,
-                                                   self._out_pinned.data_ptr(), self._stream()))
-        if self._h_bad.any():
-            bad = np.nonzero(self._h_bad)[0]
+        blk = self._free_block()
+        _lib.check(self._h, self._lib.ks_step_host(self._h, self._h_act.ctypes.data, blk["pinned"].data_ptr(),
+                                                   self._stream()))
+        if blk["bad"].any():
+            bad = np.nonzero(blk["bad"])[0]
             raise FloatingPointError(f"overflow encountered in KS state of env(s) {bad[:8].tolist()}"
                                      f"{'...' if bad.size > 8 else ''} (np.seterr(over='raise') in the reference)")
-        copy = np.array if self.copy else np.asarray
-        obs = copy(self._h_obs)
-        rewards = copy(self._h_reward)
-        steps = self._h_step.astype(np.int64)
-        truncated = self._h_trunc.astype(bool)
+        if self.copy and blk["owned"]:
+            # zero-copy: fresh view objects into a pinned block that no earlier result still uses
+            obs, rewards = blk["obs"][...], blk["reward"][...]
+        elif self.copy:
+            obs, rewards = np.array(blk["obs"]), np.array(blk["reward"])
+        else:
+            obs, rewards = blk["obs"], blk["reward"]
+        steps = blk["step"].astype(np.int64)
+        truncated = blk["trunc"].astype(bool)
         terminated = np.zeros(self.num_envs, dtype=bool)
         infos = {"step": steps, "_step": np.ones(self.num_envs, dtype=bool)}
         if truncated.any():
@@ -356,6 +358,49 @@ class KSVecEnv(VectorEnvBase):
     def step(self, actions):
         self.step_async(actions)
         return self.step_wait()
+
+    MAX_RESULT_BLOCKS = 8
+
+    def _new_block(self) -> dict:
+        """One pinned host block with the layout of ``ks_out_layout`` and typed views into it."""
+        B, o = self.num_envs, self._out_offsets
+        pinned = torch.empty(self._out_total, dtype=torch.uint8, pin_memory=torch.cuda.is_available())
+        host = pinned.numpy()
+        blk = dict(pinned=pinned, host=host, owned=True,
+                   reward=host[o[0]:o[0] + 8 * B].view(np.float64),
+                   obs=host[o[1]:o[1] + 4 * B * self.obs_len].view(np.float32).reshape(B, 1, self.obs_len),
+                   step=host[o[2]:o[2] + 4 * B].view(np.int32), trunc=host[o[3]:o[3] + B].view(np.uint8),
+                   bad=host[o[4]:o[4] + B].view(np.uint8))
+        del host, pinned
+        blk["refs"] = self._block_refs(blk)     # our own references; anything above = a result still in use
+        return blk
+
+    @staticmethod
+    def _block_refs(blk: dict) -> int:
+        return sys.getrefcount(blk["host"])
+
+    def _free_block(self) -> dict:
+        """The pinned block the next ``ks_step_host`` may DMA into.  With ``copy=True`` the arrays
+        ``step`` returns are views of such a block (reading 1 MiB back out of freshly DMA-written
+        pinned memory costs a single core ~70 us, more than the whole D2H copy), so a block is reused
+        only when no earlier result -- or any view derived from one -- still references it (NumPy's
+        base-object reference count says so).  A caller that keeps every observation alive (a replay
+        buffer of views) ends up on the last block with ``owned = False``: results are then copied
+        out, exactly like ``np.array``.  Either way a returned array is never overwritten."""
+        if not self.copy:
+            return self._blocks[0]
+        for blk in self._blocks:
+            if self._block_refs(blk) == blk["refs"]:
+                blk["owned"] = True
+                return blk
+        if len(self._blocks) < self.MAX_RESULT_BLOCKS:
+            blk = self._new_block()
+            self._blocks.append(blk)
+            return blk
+        if "spill" not in self.__dict__:
+            self.spill = self._new_block()
+        self.spill["owned"] = False
+        return self.spill
 
     def _observe(self, u: np.ndarray) -> np.ndarray:
         """float32 observation ``(B,1,No)`` of states ``u [B,N]`` (cast + sensor sampling)."""

@@ -57,3 +57,38 @@ def test_gpu_resident_rollout_matches_host_api_path():
     assert abs(float(pipe.oscaling.vmin) - lo) < 1e-6 and abs(float(pipe.oscaling.vmax) - hi) < 1e-6
     for e in (env, ref, chk):
         e.close()
+
+
+def test_dataset_export_matches_generate_py_format(tmp_path):
+    """generate.py:40-63: TensorDataset(obs, actions, nxt, rewards, terminated, truncated, steps) of full
+    random-action episodes; here with short episodes / burn-in so the step API can re-play one."""
+    import numpy as np
+    import torch
+    from model_based_pde_control_b200 import KSVecEnv
+    from model_based_pde_control_b200.dataset import generate_episodes, main
+
+    env = KSVecEnv(5, dict(Tmax=2.0, cfg_steps=50), ic="device", burnin_periods=4)     # 40-step episodes
+    T = env.max_episode_steps
+    assert T == 40
+    data = generate_episodes(env, 7, seed=3)                                            # 2 batches (5 + 2)
+    obs, actions, nxt, rewards, terminated, truncated, steps = data.tensors
+    assert obs.shape == (7, T, 1, 64) and obs.dtype == torch.float32
+    assert actions.shape == (7, T, 1, 4) and float(actions.abs().max()) <= 1.0
+    assert nxt.shape == obs.shape and rewards.shape == (7, T) and rewards.dtype == torch.float32
+    assert terminated.dtype == torch.bool and not terminated.any()
+    assert truncated.dtype == torch.bool and truncated[:, -1].all() and not truncated[:, :-1].any()
+    assert steps.dtype == torch.int64 and torch.equal(steps[3], torch.arange(T))
+    assert torch.equal(obs[:, 1:], nxt[:, :-1])
+    # replay episode 0 through the step API from its first observation's state: same trajectory
+    env2 = KSVecEnv(5, dict(Tmax=2.0, cfg_steps=50), ic="device", burnin_periods=4)
+    env2.reset_device(seed=3)
+    u0, _ = env2.get_state()
+    assert np.array_equal(u0[0].astype(np.float32), obs[0, 0, 0].numpy())
+    for t in range(3):
+        o, r, term, trunc, info = env2.step(actions[:5, t].numpy())
+        assert np.array_equal(o[:, 0], nxt[:5, t, 0].numpy()) and np.allclose(r, rewards[:5, t].numpy(), rtol=1e-6)
+    env.close(); env2.close()
+    out = tmp_path / "ks.pl"
+    assert main(["--output", str(out), "--episodes", "3", "--config", '{"Tmax": 1.0, "cfg_steps": 50}', "--seed", "1"]) == 0
+    loaded = torch.load(out, weights_only=False)
+    assert len(loaded) == 3 and loaded.tensors[0].shape == (3, 20, 1, 64)

@@ -85,3 +85,37 @@ def test_product_package_never_imports_the_oracle():
                 text = open(os.path.join(dirpath, fn)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), fn
                 assert "ks_oracle" not in text and "scipy" not in text, fn
+
+
+def test_result_blocks_are_reused_only_when_no_result_references_them():
+    """KSVecEnv.step returns views of pinned result blocks (zero-copy); a block is recycled only when
+    no earlier result, nor any view derived from one, is alive.  Host logic only -- no GPU needed."""
+    import types
+    from model_based_pde_control_b200.env import KSVecEnv
+
+    B, No = 6, 8
+    offs = [0, 48, 48 + 192, 48 + 192 + 32, 48 + 192 + 32 + 16]
+    fake = types.SimpleNamespace(num_envs=B, obs_len=No, _out_offsets=offs, _out_total=offs[4] + 16, copy=True,
+                                 MAX_RESULT_BLOCKS=3, _block_refs=KSVecEnv._block_refs)
+    fake._new_block = lambda: KSVecEnv._new_block(fake)
+    fake._blocks = [fake._new_block()]
+    free = lambda: KSVecEnv._free_block(fake)
+
+    b0 = free()
+    assert b0 is fake._blocks[0] and b0["owned"]
+    obs = b0["obs"][...]                    # what step() hands out
+    b1 = free()
+    assert b1 is not b0 and len(fake._blocks) == 2          # obs alive -> block 0 must not be overwritten
+    row = obs[2, 0]                          # a derived view keeps the block busy after `obs` is gone
+    del obs
+    assert free() is b1
+    del row
+    assert free() is b0                      # released -> recycled
+    held = []
+    for _ in range(3):                       # a caller that keeps everything
+        held.append(free()["obs"][...])
+    assert len(fake._blocks) == 3
+    spill = free()
+    assert not spill["owned"] and all(spill is not b for b in fake._blocks)   # -> copy-out path
+    del held
+    assert free()["owned"]

@@ -53,7 +53,7 @@ def main():
     np.copyto(env._h_act, a_host.reshape(B, env.J))
 
     def host_call():
-        env._lib.ks_step_host(env._h, env._h_act.ctypes.data, env._out_pinned.data_ptr(), env._stream())
+        env._lib.ks_step_host(env._h, env._h_act.ctypes.data, env._blocks[0]["pinned"].data_ptr(), env._stream())
 
     timeit("ks_step_host_ms", host_call)
     timeit("KSVecEnv_step_ms", lambda: env.step(a_host))
