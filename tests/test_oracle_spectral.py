@@ -31,7 +31,7 @@ def test_linear_propagator_is_exact():
 
 def test_agrees_with_the_reference_scheme_up_to_its_spatial_error_which_converges():
     """FD-RK4 (the reference scheme, C oracle) on N = 64, 128, 256 points of the same L = 22 domain
-    against the spectral solution on the same grid: the gap shrinks ~4x per refinement (2nd-order upwind)."""
+    against the spectral solution on the same grid: 1.1e-3, 6.3e-5, 4.5e-6 -- the gap is the FD truncation error."""
     L, T = 22.0, 0.25
     xs = lambda N: np.arange(N) * L / N
     u0f = lambda x: 1.2 * np.cos(2 * np.pi * 2 * x / L + 0.3) + 0.8 * np.sin(2 * np.pi * 3 * x / L) + 0.3 * np.cos(2 * np.pi * x / L)
@@ -43,7 +43,7 @@ def test_agrees_with_the_reference_scheme_up_to_its_spatial_error_which_converge
         u_fd, _ = ks_c.step(cfg, u0[None], np.zeros((1, N), np.float32))
         u_sp, _ = ke.step(u0, np.zeros(N), N, L, T / 50, 50)
         gaps.append(float(rel_l2(u_fd[0], u_sp)))
-    assert gaps[0] < 5e-3 and gaps[1] < gaps[0] / 2.5 and gaps[2] < gaps[1] / 2.5, gaps
+    assert gaps[0] < 5e-3 and gaps[1] < gaps[0] / 8 and gaps[2] < gaps[1] / 8, gaps
 
 
 def test_packing_two_real_fields_into_one_complex_transform_is_exact():
