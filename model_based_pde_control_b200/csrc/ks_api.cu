@@ -386,9 +386,9 @@ int ks_create(const ks_config *cfg, ks_handle **out)
     if (cfg->solver != KS_SOLVER_FD_RK4 && cfg->solver != KS_SOLVER_ETDRK4)
         return fail(nullptr, KS_ERR_ARG, "ks_create: bad solver %d", cfg->solver);
     const bool etd = cfg->solver == KS_SOLVER_ETDRK4;
-    if (etd && (cfg->N != ks::kEtdN || cfg->reward_mode != KS_REWARD_L2))
-        return fail(nullptr, KS_ERR_UNSUPPORTED, "ks_create: the spectral ETDRK4 solver supports N = %d and the L2 reward only "
-                    "(N=%d reward_mode=%d)", ks::kEtdN, cfg->N, cfg->reward_mode);
+    if (etd && ((cfg->N != 64 && cfg->N != 128 && cfg->N != 256) || cfg->reward_mode != KS_REWARD_L2))
+        return fail(nullptr, KS_ERR_UNSUPPORTED, "ks_create: the spectral ETDRK4 solver supports N = 64, 128, 256 and the L2 "
+                    "reward only (N=%d reward_mode=%d)", cfg->N, cfg->reward_mode);
 
     int P = etd ? 8 : cfg->points_per_lane;
     if (P != 0 && (P < ks::kMinP || P > ks::kMaxP || cfg->N % P || cfg->N / P > 32))
@@ -430,11 +430,13 @@ int ks_create(const ks_config *cfg, ks_handle **out)
     h->kernel = f64 ? (l2 ? ks::period_kernel_f64_l2(P) : ks::period_kernel_f64_diss(P))
                     : (l2 ? ks::period_kernel_f32_l2(P) : ks::period_kernel_f32_diss(P));
     if (etd) {
-        // a pair of envs per 8 lanes x 8 complex registers, 8 envs per warp (ks_etd.cuh)
-        h->lanes = 8;
-        h->envs_per_warp = 8;
-        h->grid = (int)((cfg->num_envs + 8 * (ks::kBlockThreads / 32) - 1) / (8 * (ks::kBlockThreads / 32)));
-        h->kernel = f64 ? ks::etd_kernel_f64() : ks::etd_kernel_f32();
+        // a pair of envs per 8R lanes x 8 complex registers (N = 64 R), 8/R envs per warp (ks_etd.cuh)
+        const int R = cfg->N / ks::kEtdN;
+        h->lanes = 8 * R;
+        h->envs_per_warp = 8 / R;
+        const int per_cta = h->envs_per_warp * (ks::kBlockThreads / 32);
+        h->grid = (int)((cfg->num_envs + per_cta - 1) / per_cta);
+        h->kernel = f64 ? ks::etd_kernel_f64(R) : ks::etd_kernel_f32(R);
     }
     const double dx = cfg->L / cfg->N;  // kuramoto.py:55
     fill_coef(h->c64, dx, cfg->dt);

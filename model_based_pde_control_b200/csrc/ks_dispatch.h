@@ -13,9 +13,9 @@ const void *period_kernel_f64_l2(int P);
 const void *period_kernel_f64_diss(int P);
 const void *period_kernel_f32_l2(int P);
 const void *period_kernel_f32_diss(int P);
-// Spectral ETDRK4 solver (ks_etd.cuh, N = 64): one kernel per precision.
-const void *etd_kernel_f64();
-const void *etd_kernel_f32();
+// Spectral ETDRK4 solver (ks_etd.cuh, N = 64 R): one kernel per precision and R in {1, 2, 4}.
+const void *etd_kernel_f64(int R);
+const void *etd_kernel_f32(int R);
 
 }  // namespace ks
 

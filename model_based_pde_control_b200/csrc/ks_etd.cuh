@@ -9,7 +9,7 @@
 // state averaged over the sub-steps (kuramoto.py:82-84,96), timestep / truncation / float32
 // observation (kuramoto.py:92-98) -- is the reference's.
 //
-// Layout (N = 64):
+// Layout (N = 64 R, R = 1, 2, 4; described for R = 1 first):
 //   * TWO environments share one complex transform: z = u_a + i u_b.  Every spectral operation of
 //     ETDRK4 is a multiplication by a real-kernel multiplier (E, E2, Q, f1..f3 real and even in k,
 //     the derivative factor i*g(k) odd and imaginary), so the packed spectrum Z = U_a + i U_b is
@@ -23,6 +23,12 @@
 //   * the transpose goes through a warp-private, padded shared-memory tile (128-bit, conflict-free
 //     both ways, only __syncwarp); the per-wavenumber tables live in shared memory as well; the
 //     state, the stage values, the twiddles and the period's forcing spectrum in registers.
+//   * N = 128 / 256 (R = 2 / 4): a pair occupies 8R lanes, x-index n = pl + 8R r.  After the four-step
+//     core (whose transpose then runs inside the 8 lanes that share pl mod R) the R lanes that differ
+//     in pl mod R are combined by one / two radix-2 butterfly stages with warp shuffles (twiddles
+//     W_8R^(m1 s) before, a -i rotation between the stages); the spectral layout becomes lane
+//     (m1', k2 = pl / R), register s  <->  k = 64 bitrev(m1') + 8 s + k2, which only the host-side
+//     table permutation needs to know.
 //   * HBM is touched at control-period boundaries only (state in, state / observation / reward out).
 #pragma once
 
@@ -30,7 +36,7 @@
 
 namespace ks {
 
-constexpr int kEtdN = 64;          // grid points handled by this kernel
+constexpr int kEtdN = 64;          // grid points of the base layout; the kernel handles N = 64 R, R = 1, 2, 4
 // Per-wavenumber tables, each [N] in natural FFT order (host-precomputed, ks_api.cu).  The kernel
 // carries the nonlinear terms pre-multiplied by Q (N~ = Q N), which removes Q from the stage
 // formulas; the final combination then needs f1/Q, 2 f2/Q, f3/Q (Q = h phi_1(hL/2)/2 > 0).
@@ -111,42 +117,119 @@ __device__ __forceinline__ void transpose8(T (&x)[8], T (&y)[8], C2<T> *tile, in
     __syncwarp();
 }
 
-// physical (lane n1, reg n2: n = n1 + 8 n2)  ->  spectral (lane k2, reg k1: k = 8 k1 + k2), unnormalised
+// R-point DFT across the R adjacent lanes that share pl / R (R = 2, 4), radix-2 butterflies with
+// warp shuffles, decimation in frequency: the result index ends up bit-reversed in the lane
+// position, which the host-side table permutation accounts for.  `inv_core` is the mirrored
+// sequence; called with x and y exchanged it is the exact inverse (up to the factor R).
 template <typename T>
-__device__ __forceinline__ void fft64(T (&x)[8], T (&y)[8], const T (&twx)[8], const T (&twy)[8], C2<T> *tile, int l)
+__device__ __forceinline__ void lane_butterfly(T (&x)[8], T (&y)[8], int xor_mask, T sgn)
+{
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        const T px = __shfl_xor_sync(kFullMask, x[r], xor_mask), py = __shfl_xor_sync(kFullMask, y[r], xor_mask);
+        x[r] = fma_t<T>(sgn, x[r], px);       // lower lane: a + b,  upper lane: a - b (own value is b)
+        y[r] = fma_t<T>(sgn, y[r], py);
+    }
+}
+template <typename T>
+__device__ __forceinline__ void rotate_minus_i(T (&x)[8], T (&y)[8], bool on)
+{
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+        const T a = x[r], b = y[r];
+        x[r] = on ? b : a;                     // (a + i b)(-i) = b - i a
+        y[r] = on ? -a : b;
+    }
+}
+template <typename T, int R>
+__device__ __forceinline__ void lanes_fwd(T (&x)[8], T (&y)[8], int m1)
+{
+    if constexpr (R == 2) {
+        lane_butterfly<T>(x, y, 1, (m1 & 1) ? T(-1) : T(1));
+    } else if constexpr (R == 4) {
+        lane_butterfly<T>(x, y, 2, (m1 & 2) ? T(-1) : T(1));
+        rotate_minus_i<T>(x, y, m1 == 3);     // W4^(m1 & 1) on the difference lanes
+        lane_butterfly<T>(x, y, 1, (m1 & 1) ? T(-1) : T(1));
+    }
+}
+template <typename T, int R>
+__device__ __forceinline__ void lanes_inv_core(T (&x)[8], T (&y)[8], int m1)
+{
+    if constexpr (R == 2) {
+        lane_butterfly<T>(x, y, 1, (m1 & 1) ? T(-1) : T(1));
+    } else if constexpr (R == 4) {
+        lane_butterfly<T>(x, y, 1, (m1 & 1) ? T(-1) : T(1));
+        rotate_minus_i<T>(x, y, m1 == 3);
+        lane_butterfly<T>(x, y, 2, (m1 & 2) ? T(-1) : T(1));
+    }
+}
+// (x + i y)[s] *= W_8R^(m1 s), s = 1..7, from the small shared table twb[m1][s]
+template <typename T>
+__device__ __forceinline__ void twiddle_lanes(T (&x)[8], T (&y)[8], const C2<T> *twb_row)
+{
+#pragma unroll
+    for (int r = 1; r < 8; ++r) {
+        const C2<T> w = twb_row[r];
+        const T a = x[r], b = y[r];
+        x[r] = fma_t<T>(a, w.x, -(b * w.y));
+        y[r] = fma_t<T>(a, w.y, b * w.x);
+    }
+}
+
+// What a lane needs for its share of a transform: twiddles W_N^(pl r) (registers), its 8-lane
+// transpose group's tile and its position `l` = pl / R in that group, and for R > 1 its row
+// W_8R^(m1 s) of the small shared twiddle table with m1 = pl % R.
+template <typename T>
+struct FftCtx {
+    T twx[8], twy[8];
+    C2<T> *tile;
+    const C2<T> *twb_row;
+    int l, m1;
+};
+
+// physical (lane pl, reg r: n = pl + 8R r)  ->  spectral, unnormalised
+template <typename T, int R>
+__device__ __forceinline__ void fft64(T (&x)[8], T (&y)[8], const FftCtx<T> &c)
 {
     fft8<T>(x, y);
-    twiddle8<T>(x, y, twx, twy);
-    transpose8<T>(x, y, tile, l);
+    twiddle8<T>(x, y, c.twx, c.twy);
+    transpose8<T>(x, y, c.tile, c.l);
     fft8<T>(x, y);
+    if constexpr (R > 1) {
+        twiddle_lanes<T>(x, y, c.twb_row);
+        lanes_fwd<T, R>(x, y, c.m1);
+    }
 }
 // spectral -> physical, unnormalised (x/y exchanged = conjugated kernel)
-template <typename T>
-__device__ __forceinline__ void ifft64(T (&x)[8], T (&y)[8], const T (&twx)[8], const T (&twy)[8], C2<T> *tile, int l)
+template <typename T, int R>
+__device__ __forceinline__ void ifft64(T (&x)[8], T (&y)[8], const FftCtx<T> &c)
 {
+    if constexpr (R > 1) {
+        lanes_inv_core<T, R>(y, x, c.m1);
+        twiddle_lanes<T>(y, x, c.twb_row);
+    }
     fft8<T>(y, x);
-    transpose8<T>(x, y, tile, l);
-    twiddle8<T>(y, x, twx, twy);
+    transpose8<T>(x, y, c.tile, c.l);
+    twiddle8<T>(y, x, c.twx, c.twy);
     fft8<T>(y, x);
 }
 
 // Table values for this lane's registers m = 2h, 2h+1 (k = 8 m + j), one 2-element vector load.
-// Layout in shared memory: [table][h][lane j].
-template <typename T>
-__device__ __forceinline__ C2<T> tab2(const C2<T> *tab, int which, int h, int l)
+// Layout in shared memory: [table][h][lane pl of the pair], LP = 8R lanes.
+template <typename T, int LP>
+__device__ __forceinline__ C2<T> tab2(const C2<T> *tab, int which, int h, int pl)
 {
-    return tab[(which * 4 + h) * 8 + l];
+    return tab[(which * 4 + h) * LP + pl];
 }
 
 // Spectral right-hand side without the linear part, pre-multiplied by Q, in place:
 //   w <- i (Q g / N) * FFT( (Re/Im IFFT(w))^2 ) + Q phi_hat / N        (both packed fields at once)
 // With FIRST the squares of the physical values are the pre-step reward terms (kuramoto.py:84).
-template <typename T, bool FIRST>
-__device__ __forceinline__ void nonlinear(T (&wx)[8], T (&wy)[8], const T (&twx)[8], const T (&twy)[8], C2<T> *tile,
-                                          const C2<T> *tab, const T (&phx)[8], const T (&phy)[8], int l, T &racc_a,
-                                          T &racc_b)
+template <typename T, int R, bool FIRST>
+__device__ __forceinline__ void nonlinear(T (&wx)[8], T (&wy)[8], const FftCtx<T> &ctx, const C2<T> *tab,
+                                          const T (&phx)[8], const T (&phy)[8], int pl, T &racc_a, T &racc_b)
 {
-    ifft64<T>(wx, wy, twx, twy, tile, l);
+    ifft64<T, R>(wx, wy, ctx);
 #pragma unroll
     for (int r = 0; r < 8; ++r) {
         wx[r] = wx[r] * wx[r];
@@ -156,10 +239,10 @@ __device__ __forceinline__ void nonlinear(T (&wx)[8], T (&wy)[8], const T (&twx)
         racc_a += ((wx[0] + wx[1]) + (wx[2] + wx[3])) + ((wx[4] + wx[5]) + (wx[6] + wx[7]));
         racc_b += ((wy[0] + wy[1]) + (wy[2] + wy[3])) + ((wy[4] + wy[5]) + (wy[6] + wy[7]));
     }
-    fft64<T>(wx, wy, twx, twy, tile, l);
+    fft64<T, R>(wx, wy, ctx);
 #pragma unroll
     for (int h = 0; h < 4; ++h) {
-        const C2<T> g = tab2<T>(tab, kTabG, h, l);
+        const C2<T> g = tab2<T, 8 * R>(tab, kTabG, h, pl);
         const T re0 = wx[2 * h], im0 = wy[2 * h], re1 = wx[2 * h + 1], im1 = wy[2 * h + 1];
         wx[2 * h] = fma_t<T>(-g.x, im0, phx[2 * h]);
         wy[2 * h] = fma_t<T>(g.x, re0, phy[2 * h]);
@@ -174,24 +257,37 @@ struct EtdParams {
 };
 
 // ---------------------------------------------------------------------------------------------
-// The spectral control-period kernel: K periods x cfg_steps ETDRK4 steps, 8 envs per warp.
+// The spectral control-period kernel: K periods x cfg_steps ETDRK4 steps, 8/R envs per warp.
 // ---------------------------------------------------------------------------------------------
-template <typename T>
+template <typename T, int R>
 __global__ void __launch_bounds__(kBlockThreads) ks_etd_kernel(const EtdParams ep)
 {
+    static_assert(R == 1 || R == 2 || R == 4, "N = 64 R with R = 1, 2, 4");
     const Params &p = ep.p;
-    constexpr int N = kEtdN;
+    constexpr int N = kEtdN * R;
+    constexpr int LP = 8 * R;                       // lanes per env pair
+    constexpr int PPW = 4 / R;                      // env pairs per warp
     constexpr int kWarps = kBlockThreads / 32;
-    __shared__ C2<T> s_tab[kEtdTables * 4 * 8];
-    __shared__ C2<T> s_tile[kWarps][4 * 72];
+    constexpr int kBlk = R == 1 ? 72 : 72 + 8 / R;  // tile stride of an 8-lane transpose group (bank-conflict free)
+    __shared__ C2<T> s_tab[kEtdTables * 4 * LP];
+    __shared__ C2<T> s_tile[kWarps][4 * kBlk];
+    __shared__ C2<T> s_twb[R * 8];                  // W_8R^(m1 s)
 
-    // per-wavenumber tables -> shared memory in register-pair layout (k = 8 m + j)
+    // per-wavenumber tables -> shared memory.  Slot (table, h, pl, q) belongs to lane pl, register
+    // s = 2h + q, i.e. wavenumber index k = 64 bitrev_R(pl % R) + 8 s + pl / R.
     {
         const T *src = static_cast<const T *>(ep.tables);
-        for (int i = threadIdx.x; i < kEtdTables * N; i += kBlockThreads) {
-            const int t = i / N, k = i % N, m = k >> 3, j = k & 7;
-            T *dst = reinterpret_cast<T *>(&s_tab[(t * 4 + (m >> 1)) * 8 + j]);
-            dst[m & 1] = src[i];
+        for (int i = threadIdx.x; i < kEtdTables * 4 * LP * 2; i += kBlockThreads) {
+            const int q = i & 1, pl_ = (i >> 1) % LP, h = ((i >> 1) / LP) & 3, t = (i >> 1) / (4 * LP);
+            const int m1p = pl_ % R, k2 = pl_ / R;
+            const int j1 = R == 4 ? ((m1p & 1) << 1 | (m1p >> 1)) : m1p;
+            const int k = 64 * j1 + 8 * (2 * h + q) + k2;
+            reinterpret_cast<T *>(&s_tab[(t * 4 + h) * LP + pl_])[q] = src[t * N + k];
+        }
+        for (int i = threadIdx.x; i < R * 8; i += kBlockThreads) {
+            double sn, cs;
+            sincospi(-2.0 * (double)((i >> 3) * (i & 7)) / (double)LP, &sn, &cs);
+            s_twb[i] = C2<T>{(T)cs, (T)sn};
         }
     }
     __syncthreads();
@@ -199,8 +295,8 @@ __global__ void __launch_bounds__(kBlockThreads) ks_etd_kernel(const EtdParams e
     const int lane = threadIdx.x & 31;
     const int wib = threadIdx.x >> 5;
     const int warp = (blockIdx.x * kBlockThreads + threadIdx.x) >> 5;
-    const int grp = lane >> 3, l = lane & 7;
-    const int envA = (warp * 4 + grp) * 2, envB = envA + 1;
+    const int grp = lane / LP, pl = lane % LP;      // pair slot in the warp, lane inside the pair
+    const int envA = (warp * PPW + grp) * 2, envB = envA + 1;
     bool actA = envA < p.B, actB = envB < p.B;
     if (p.mask != nullptr) {
         actA = actA && p.mask[envA] != 0;
@@ -208,27 +304,29 @@ __global__ void __launch_bounds__(kBlockThreads) ks_etd_kernel(const EtdParams e
     }
     if (__ballot_sync(kFullMask, actA || actB) == 0u) return;   // warp-uniform (after the only __syncthreads)
 
-    C2<T> *tile = &s_tile[wib][grp * 72];
     const C2<T> *tab = s_tab;
-
-    // twiddles W64^(l r) = exp(-2 pi i l r / 64)
-    T twx[8], twy[8];
+    FftCtx<T> ctx;
+    ctx.m1 = pl % R;
+    ctx.l = pl / R;
+    ctx.tile = &s_tile[wib][(grp * R + ctx.m1) * kBlk];
+    ctx.twb_row = &s_twb[ctx.m1 * 8];
+    // twiddles W_N^(pl r) = exp(-2 pi i pl r / N)
 #pragma unroll
     for (int r = 0; r < 8; ++r) {
         double sn, cs;
-        sincospi(-(double)(l * r) / 32.0, &sn, &cs);
-        twx[r] = (T)cs;
-        twy[r] = (T)sn;
+        sincospi(-2.0 * (double)(pl * r) / (double)N, &sn, &cs);
+        ctx.twx[r] = (T)cs;
+        ctx.twy[r] = (T)sn;
     }
 
     // physical state of the pair: x = env A, y = env B (idle slots integrate zeros, never stored)
     T ux[8], uy[8];
-    T *ua = static_cast<T *>(p.u) + (size_t)(actA ? envA : 0) * N + l;
-    T *ub = static_cast<T *>(p.u) + (size_t)(actB ? envB : 0) * N + l;
+    T *ua = static_cast<T *>(p.u) + (size_t)(actA ? envA : 0) * N + pl;
+    T *ub = static_cast<T *>(p.u) + (size_t)(actB ? envB : 0) * N + pl;
 #pragma unroll
     for (int r = 0; r < 8; ++r) {
-        ux[r] = actA ? ua[8 * r] : T(0);
-        uy[r] = actB ? ub[8 * r] : T(0);
+        ux[r] = actA ? ua[LP * r] : T(0);
+        uy[r] = actB ? ub[LP * r] : T(0);
     }
     int tsA = actA ? p.timestep[envA] : 0, tsB = actB ? p.timestep[envB] : 0;
     bool badA = actA ? p.nonfinite[envA] != 0 : false, badB = actB ? p.nonfinite[envB] != 0 : false;
@@ -242,8 +340,8 @@ __global__ void __launch_bounds__(kBlockThreads) ks_etd_kernel(const EtdParams e
             if (p.phi != nullptr) {
 #pragma unroll
                 for (int r = 0; r < 8; ++r) {
-                    fx[r] = actA ? T(p.phi[(size_t)envA * N + l + 8 * r]) : T(0);
-                    fy[r] = actB ? T(p.phi[(size_t)envB * N + l + 8 * r]) : T(0);
+                    fx[r] = actA ? T(p.phi[(size_t)envA * N + pl + LP * r]) : T(0);
+                    fy[r] = actB ? T(p.phi[(size_t)envB * N + pl + LP * r]) : T(0);
                 }
             } else if (p.actions != nullptr) {
                 const float *aA = p.actions + ((size_t)k * p.B + (actA ? envA : 0)) * p.J;
@@ -255,7 +353,7 @@ __global__ void __launch_bounds__(kBlockThreads) ks_etd_kernel(const EtdParams e
                     const float a = __ldg(aA + j), b = __ldg(aB + j);
 #pragma unroll
                     for (int r = 0; r < 8; ++r) {
-                        const float f = __ldg(p.F + (size_t)j * N + l + 8 * r);
+                        const float f = __ldg(p.F + (size_t)j * N + pl + LP * r);
                         fa[r] = __fmaf_rn(a, f, fa[r]);
                         fb[r] = __fmaf_rn(b, f, fb[r]);
                     }
@@ -269,20 +367,22 @@ __global__ void __launch_bounds__(kBlockThreads) ks_etd_kernel(const EtdParams e
 #pragma unroll
                 for (int r = 0; r < 8; ++r) fx[r] = fy[r] = T(0);
             }
-            fft64<T>(fx, fy, twx, twy, tile, l);
+            fft64<T, R>(fx, fy, ctx);
 #pragma unroll
             for (int h = 0; h < 4; ++h) {
-                const C2<T> qn = tab2<T>(tab, kTabQN, h, l);
+                const C2<T> qn = tab2<T, LP>(tab, kTabQN, h, pl);
                 fx[2 * h] *= qn.x; fy[2 * h] *= qn.x;
                 fx[2 * h + 1] *= qn.y; fy[2 * h + 1] *= qn.y;
             }
         }
 
-        // ---- spectrum of the state, normalised: v = FFT(u) / N
+        // ---- spectrum of the state, normalised: v = FFT(u) / N.  An idle slot (odd batch, masked
+        // env) restarts from exact zeros every period, so that its rounding-level leakage into the
+        // partner does not depend on how many periods a launch covers (rollout == repeated steps).
         T vx[8], vy[8];
 #pragma unroll
-        for (int r = 0; r < 8; ++r) { vx[r] = ux[r]; vy[r] = uy[r]; }
-        fft64<T>(vx, vy, twx, twy, tile, l);
+        for (int r = 0; r < 8; ++r) { vx[r] = actA ? ux[r] : T(0); vy[r] = actB ? uy[r] : T(0); }
+        fft64<T, R>(vx, vy, ctx);
 #pragma unroll
         for (int m = 0; m < 8; ++m) { vx[m] *= invN; vy[m] *= invN; }
 
@@ -295,11 +395,11 @@ __global__ void __launch_bounds__(kBlockThreads) ks_etd_kernel(const EtdParams e
             // N~v
 #pragma unroll
             for (int m = 0; m < 8; ++m) { nx[m] = vx[m]; ny[m] = vy[m]; }
-            nonlinear<T, true>(nx, ny, twx, twy, tile, tab, phx, phy, l, racc_a, racc_b);
+            nonlinear<T, R, true>(nx, ny, ctx, tab, phx, phy, pl, racc_a, racc_b);
             // a = E2 v + N~v
 #pragma unroll
             for (int h = 0; h < 4; ++h) {
-                const C2<T> e2 = tab2<T>(tab, kTabE2, h, l);
+                const C2<T> e2 = tab2<T, LP>(tab, kTabE2, h, pl);
 #pragma unroll
                 for (int q = 0; q < 2; ++q) {
                     const int m = 2 * h + q;
@@ -309,12 +409,12 @@ __global__ void __launch_bounds__(kBlockThreads) ks_etd_kernel(const EtdParams e
                 }
             }
             // N~a
-            nonlinear<T, false>(wx, wy, twx, twy, tile, tab, phx, phy, l, dummy, dummy);
+            nonlinear<T, R, false>(wx, wy, ctx, tab, phx, phy, pl, dummy, dummy);
             // b = (a - N~v) + N~a (-> w);   a <- E2 a - N~v;   v <- E v + (f1/Q) N~v + (2 f2/Q) N~a
 #pragma unroll
             for (int h = 0; h < 4; ++h) {
-                const C2<T> e2 = tab2<T>(tab, kTabE2, h, l), e = tab2<T>(tab, kTabE, h, l);
-                const C2<T> r1 = tab2<T>(tab, kTabR1, h, l), r22 = tab2<T>(tab, kTabR22, h, l);
+                const C2<T> e2 = tab2<T, LP>(tab, kTabE2, h, pl), e = tab2<T, LP>(tab, kTabE, h, pl);
+                const C2<T> r1 = tab2<T, LP>(tab, kTabR1, h, pl), r22 = tab2<T, LP>(tab, kTabR22, h, pl);
 #pragma unroll
                 for (int q = 0; q < 2; ++q) {
                     const int m = 2 * h + q;
@@ -329,11 +429,11 @@ __global__ void __launch_bounds__(kBlockThreads) ks_etd_kernel(const EtdParams e
                 }
             }
             // N~b
-            nonlinear<T, false>(wx, wy, twx, twy, tile, tab, phx, phy, l, dummy, dummy);
+            nonlinear<T, R, false>(wx, wy, ctx, tab, phx, phy, pl, dummy, dummy);
             // v += (2 f2/Q) N~b;   c = (E2 a - N~v) + 2 N~b (-> w)
 #pragma unroll
             for (int h = 0; h < 4; ++h) {
-                const C2<T> r22 = tab2<T>(tab, kTabR22, h, l);
+                const C2<T> r22 = tab2<T, LP>(tab, kTabR22, h, pl);
 #pragma unroll
                 for (int q = 0; q < 2; ++q) {
                     const int m = 2 * h + q;
@@ -345,10 +445,10 @@ __global__ void __launch_bounds__(kBlockThreads) ks_etd_kernel(const EtdParams e
                 }
             }
             // N~c;   v += (f3/Q) N~c
-            nonlinear<T, false>(wx, wy, twx, twy, tile, tab, phx, phy, l, dummy, dummy);
+            nonlinear<T, R, false>(wx, wy, ctx, tab, phx, phy, pl, dummy, dummy);
 #pragma unroll
             for (int h = 0; h < 4; ++h) {
-                const C2<T> r3 = tab2<T>(tab, kTabR3, h, l);
+                const C2<T> r3 = tab2<T, LP>(tab, kTabR3, h, pl);
                 vx[2 * h] = fma_t<T>(r3.x, wx[2 * h], vx[2 * h]);
                 vy[2 * h] = fma_t<T>(r3.x, wy[2 * h], vy[2 * h]);
                 vx[2 * h + 1] = fma_t<T>(r3.y, wx[2 * h + 1], vx[2 * h + 1]);
@@ -359,7 +459,7 @@ __global__ void __launch_bounds__(kBlockThreads) ks_etd_kernel(const EtdParams e
         // ---- back to physical space
 #pragma unroll
         for (int m = 0; m < 8; ++m) { ux[m] = vx[m]; uy[m] = vy[m]; }
-        ifft64<T>(ux, uy, twx, twy, tile, l);
+        ifft64<T, R>(ux, uy, ctx);
 
         // ---- period epilogue: reward, flags, observation (kuramoto.py:92-98)
         double ra = (double)racc_a, rb = (double)racc_b;
@@ -370,39 +470,39 @@ __global__ void __launch_bounds__(kBlockThreads) ks_etd_kernel(const EtdParams e
             bB |= !(fabs((double)uy[r]) <= 1.7976931348623157e308);
         }
 #pragma unroll
-        for (int o = 4; o > 0; o >>= 1) {      // fixed-order reduction over the 8 lanes of the pair
+        for (int o = LP / 2; o > 0; o >>= 1) {  // fixed-order reduction over the lanes of the pair
             ra += __shfl_xor_sync(kFullMask, ra, o);
             rb += __shfl_xor_sync(kFullMask, rb, o);
         }
-        const unsigned gmask = 0xffu << (grp * 8);
+        const unsigned gmask = (LP == 32 ? kFullMask : ((1u << LP) - 1u)) << (grp * LP);
         const bool anyA = (__ballot_sync(kFullMask, bA) & gmask) != 0u;
         const bool anyB = (__ballot_sync(kFullMask, bB) & gmask) != 0u;
         tsA += 1;
         tsB += 1;
         if (p.obs != nullptr) {
             if (p.obs_stride <= 1) {
-                float *oa = p.obs + ((size_t)k * p.B + envA) * N + l;
-                float *ob = p.obs + ((size_t)k * p.B + envB) * N + l;
+                float *oa = p.obs + ((size_t)k * p.B + envA) * N + pl;
+                float *ob = p.obs + ((size_t)k * p.B + envB) * N + pl;
 #pragma unroll
                 for (int r = 0; r < 8; ++r) {
-                    if (actA) oa[8 * r] = (float)ux[r];
-                    if (actB) ob[8 * r] = (float)uy[r];
+                    if (actA) oa[LP * r] = (float)ux[r];
+                    if (actB) ob[LP * r] = (float)uy[r];
                 }
                 if (p.n_remote > 0) {
-                    // gather mode: stage the warp's 8 rows (512 floats, contiguous in the batch) in the
+                    // gather mode: stage the warp's rows (512 floats, contiguous in the batch) in the
                     // transpose tile and mirror them to the peers as coalesced 16-byte-per-lane stores
                     float *stg = reinterpret_cast<float *>(&s_tile[wib][0]);
                     __syncwarp();
 #pragma unroll
                     for (int r = 0; r < 8; ++r) {
-                        stg[(2 * grp) * N + l + 8 * r] = (float)ux[r];
-                        stg[(2 * grp + 1) * N + l + 8 * r] = (float)uy[r];
+                        stg[(2 * grp) * N + pl + LP * r] = (float)ux[r];
+                        stg[(2 * grp + 1) * N + pl + LP * r] = (float)uy[r];
                     }
                     __syncwarp();
-                    float *wbase = p.obs + ((size_t)k * p.B + (size_t)warp * 8) * N;
+                    float *wbase = p.obs + ((size_t)k * p.B + (size_t)warp * (2 * PPW)) * N;
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
-                        const int i4 = j * 32 + lane, e = warp * 8 + (i4 * 4) / N;     // env that owns this float4
+                        const int i4 = j * 32 + lane, e = warp * (2 * PPW) + (i4 * 4) / N;     // env that owns this float4
                         if (e >= p.B || (p.mask != nullptr && p.mask[e] == 0)) continue;
                         const float4 v = *reinterpret_cast<const float4 *>(stg + i4 * 4);
                         for (int q = 0; q < p.n_remote; ++q)
@@ -414,7 +514,7 @@ __global__ void __launch_bounds__(kBlockThreads) ks_etd_kernel(const EtdParams e
                 const int first = p.obs_stride / 2;
 #pragma unroll
                 for (int r = 0; r < 8; ++r) {
-                    const int idx = l + 8 * r - first;
+                    const int idx = pl + LP * r - first;
                     if (idx >= 0 && idx % p.obs_stride == 0) {
                         float *da = p.obs + ((size_t)k * p.B + envA) * p.obs_len + idx / p.obs_stride;
                         float *db = p.obs + ((size_t)k * p.B + envB) * p.obs_len + idx / p.obs_stride;
@@ -428,7 +528,7 @@ __global__ void __launch_bounds__(kBlockThreads) ks_etd_kernel(const EtdParams e
                 }
             }
         }
-        if (l == 0) {
+        if (pl == 0) {
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
                 const bool act = e ? actB : actA;
@@ -457,10 +557,10 @@ __global__ void __launch_bounds__(kBlockThreads) ks_etd_kernel(const EtdParams e
 
 #pragma unroll
     for (int r = 0; r < 8; ++r) {
-        if (actA) ua[8 * r] = ux[r];
-        if (actB) ub[8 * r] = uy[r];
+        if (actA) ua[LP * r] = ux[r];
+        if (actB) ub[LP * r] = uy[r];
     }
-    if (l == 0) {
+    if (pl == 0) {
         if (actA) p.timestep[envA] = p.reset_timestep ? 0 : tsA;
         if (actB) p.timestep[envB] = p.reset_timestep ? 0 : tsB;
     }

@@ -61,6 +61,44 @@ def test_one_period_vs_oracle(B):
     env.close()
 
 
+@pytest.mark.parametrize("N,L,J,B,precision", [(128, 44.0, 4, 9, "f64"), (256, 88.0, 8, 7, "f64"), (256, 88.0, 8, 64, "f64"),
+                                                 (128, 44.0, 4, 33, "f32"), (256, 88.0, 8, 10, "f32"),
+                                                 (256, 22.0, 4, 5, "f64")])
+def test_larger_grids_vs_oracle(N, L, J, B, precision):
+    """N = 128 / 256: the four-step core plus radix-2 / radix-4 shuffle butterflies across lanes
+    (large-domain configuration L = 88, 8 jets; and a finer grid on the default domain)."""
+    from model_based_pde_control_b200 import KSVecEnv
+
+    rng = np.random.default_rng(N + B)
+    dt, steps = (0.025, 10) if L / N > 0.3 else (0.0125, 20)
+    env = KSVecEnv(B, dict(N=N, L=L, dt=dt, cfg_steps=steps), Xi=[k / J for k in range(J)], solver="etdrk4",
+                   precision=precision)
+    u0 = np.concatenate([smooth_states(rng, B, 64)] * (N // 64), axis=1) * 0.7 + rng.uniform(-0.2, 0.2, (B, N))
+    if precision == "f32":
+        u0 = u0.astype(np.float32).astype(np.float64)
+    a = rng.uniform(-1, 1, (B, 1, J)).astype(np.float32)
+    env.set_state(u0, 0)
+    obs, rew, term, trunc, info = env.step(a)
+    u1, ts = env.get_state()
+    u_ref, r_ref = oracle_step(env, u0, a)
+    tol = TOL64 if precision == "f64" else TOL32
+    assert rel_l2(u1, u_ref).max() <= tol, rel_l2(u1, u_ref).max()
+    assert np.abs((rew - r_ref) / r_ref).max() <= tol
+    assert np.array_equal(obs[:, 0], u1.astype(np.float32)) and (ts == 1).all()
+    # K periods in one launch == K steps, also on the larger grids
+    import torch
+    acts = torch.as_tensor(rng.uniform(-1, 1, (3, B, J)).astype(np.float32)).cuda()
+    env.set_state(u0, 0)
+    env.rollout_device(acts)
+    ur, _ = env.get_state()
+    env.set_state(u0, 0)
+    for k in range(3):
+        env.step_device(acts[k])
+    us, _ = env.get_state()
+    assert np.array_equal(ur, us)
+    env.close()
+
+
 def test_rough_initial_condition_and_no_dealias():
     """White-noise states (every mode excited, as the reset's U(-0.4,0.4) draw) with and without the 2/3 rule."""
     rng = np.random.default_rng(5)
