@@ -36,20 +36,34 @@ class ScaleTransformDevice:
         self.vmax = None if bounds[1] is None else torch.as_tensor(bounds[1], dtype=torch.float32).amax()
         self.frozen = frozen
 
+    def _on(self, device):
+        """Keep the running bounds on the data's device (a per-call ``.to`` of a CPU scalar is a
+        synchronous pageable copy)."""
+        if self.vmin is not None and self.vmin.device != device:
+            self.vmin = self.vmin.to(device)
+        if self.vmax is not None and self.vmax.device != device:
+            self.vmax = self.vmax.to(device)
+
     def update(self, values: torch.Tensor) -> None:
         if self.frozen:
             return
-        lo, hi = values.amin().to(torch.float32), values.amax().to(torch.float32)
-        self.vmin = lo if self.vmin is None else torch.minimum(lo, self.vmin.to(lo.device))
-        self.vmax = hi if self.vmax is None else torch.maximum(hi, self.vmax.to(hi.device))
+        self._on(values.device)
+        lo, hi = torch.aminmax(values)
+        lo, hi = lo.to(torch.float32), hi.to(torch.float32)
+        # in place once the bounds exist: a captured CUDA graph keeps pointing at these tensors
+        if self.vmin is None:
+            self.vmin, self.vmax = lo.clone(), hi.clone()
+        else:
+            torch.minimum(lo, self.vmin, out=self.vmin)
+            torch.maximum(hi, self.vmax, out=self.vmax)
 
     def __call__(self, values: torch.Tensor) -> torch.Tensor:
-        vmin, vmax = self.vmin.to(values.device), self.vmax.to(values.device)
-        return (values - vmin) / (vmax - vmin) * (self.upper - self.lower) + self.lower
+        self._on(values.device)
+        return (values - self.vmin) / (self.vmax - self.vmin) * (self.upper - self.lower) + self.lower
 
     def inverse(self, values: torch.Tensor) -> torch.Tensor:
-        vmin, vmax = self.vmin.to(values.device), self.vmax.to(values.device)
-        return (values - self.lower) / (self.upper - self.lower) * (vmax - vmin) + vmin
+        self._on(values.device)
+        return (values - self.lower) / (self.upper - self.lower) * (self.vmax - self.vmin) + self.vmin
 
 
 class SensorTransformDevice:
@@ -93,37 +107,61 @@ class DeviceEnvPipeline:
         self.oscaling = ScaleTransformDevice(scale=obs_scale, frozen=frozen_obs_scaling)
         self.ascaling = ScaleTransformDevice(scale=(-1.0, 1.0), bounds=action_bounds, frozen=True)
         self.agent_sensor = SensorTransformDevice(agent_sensor_stride)
-        self.obs_store = self.finals = self.obs_mask = None
-        self.act_store = self.act_mask = None
+        self.obs_store = self.finals = self.act_store = None
+        self._obs_row = self._act_row = None
+        self._rollout_buf = {}
+        self._graphs = {}
         self._episode_step = None          # host-side step counter (all envs synchronous)
         self._pending_final = None
 
     # -- StoreNObsVecWrapper -------------------------------------------------------------------
+    # All envs of the batch run synchronous fixed-length episodes (the reference relies on that too,
+    # vec_wrappers.py:26-30), so the validity masks of the stores have identical rows: they are kept
+    # on the HOST as one row each, and every masked read below is a plain slice -- no boolean
+    # indexing, hence no device->host synchronisation anywhere in a rollout.
     def _ostore_reset(self, obs):
         self.obs_store = obs.unsqueeze(1).repeat(1, self.num_steps, *([1] * (obs.dim() - 1))).clone()
         self.finals = torch.zeros_like(self.obs_store)
-        self.obs_mask = torch.zeros((self.B, self.num_steps), dtype=torch.bool, device=obs.device)
-        self.obs_mask[:, -1] = True
+        self._obs_row = [False] * (self.num_steps - 1) + [True]
 
-    def _ostore_step(self, obs, final_obs, final_mask):
+    def _ostore_step(self, obs, final_obs):
         if final_obs is not None:
-            self.finals[final_mask] = final_obs[final_mask].unsqueeze(1)
-            self.obs_mask[final_mask] = False
+            self.finals[:] = final_obs.unsqueeze(1)
+            self._obs_row = [False] * self.num_steps
         self.obs_store[:, 0] = obs
-        self.obs_store = torch.roll(self.obs_store, -1, dims=1)
-        self.obs_mask[:, 0] = True
-        self.obs_mask = torch.roll(self.obs_mask, -1, dims=1)
+        self._obs_row[0] = True
+        if self.num_steps > 1:
+            self.obs_store = torch.roll(self.obs_store, -1, dims=1)
+            self._obs_row = self._obs_row[1:] + self._obs_row[:1]
+
+    @property
+    def obs_mask(self) -> torch.Tensor:
+        """``StoreNObsVecWrapper.mask`` (B, num_steps) -- materialised on request only."""
+        return torch.tensor(self._obs_row, dtype=torch.bool, device=self.obs_store.device).repeat(self.B, 1)
 
     # -- StoreNActionsVecWrapper ---------------------------------------------------------------
     def _astore_reset(self, like):
         self.act_store = torch.zeros((self.B, self.num_steps, 1, self.env.J), dtype=torch.float32, device=like.device)
-        self.act_mask = torch.zeros((self.B, self.num_steps), dtype=torch.bool, device=like.device)
+        self._act_row = [False] * self.num_steps
 
     def _astore_step(self, actions):
         self.act_store[:, 0] = actions
-        self.act_mask[:, 0] = True
-        self.act_store = torch.roll(self.act_store, -1, dims=1)
-        self.act_mask = torch.roll(self.act_mask, -1, dims=1)
+        self._act_row[0] = True
+        if self.num_steps > 1:
+            self.act_store = torch.roll(self.act_store, -1, dims=1)
+            self._act_row = self._act_row[1:] + self._act_row[:1]
+
+    @property
+    def act_mask(self) -> torch.Tensor:
+        return torch.tensor(self._act_row, dtype=torch.bool, device=self.act_store.device).repeat(self.B, 1)
+
+    @staticmethod
+    def _valid(store: torch.Tensor, row) -> torch.Tensor:
+        """``store[mask].reshape(B, n_valid, ...)`` for a mask whose rows all equal ``row`` (a copy)."""
+        idx = [i for i, v in enumerate(row) if v]
+        if idx == list(range(idx[0], idx[-1] + 1)):
+            return store[:, idx[0]:idx[-1] + 1].clone()
+        return store[:, idx]
 
     # -- the stack -----------------------------------------------------------------------------
     def _env_obs(self):
@@ -162,9 +200,9 @@ class DeviceEnvPipeline:
             self.env.reset_device(seed=None)                            # gym auto-reset (800-period burn-in)
             obs = self._env_obs()
             self._episode_step = 0
-        self._ostore_step(obs, final_obs, final_mask)
+        self._ostore_step(obs, final_obs)
         if final_obs is not None:
-            self.act_mask[final_mask, :-1] = False                      # StoreNActionsVecWrapper.step_wait
+            self._act_row = [False] * (self.num_steps - 1) + self._act_row[-1:]    # StoreNActionsVecWrapper.step_wait
         self.oscaling.update(obs)
         scaled = self.oscaling(obs)
         if final_obs is not None:
@@ -177,26 +215,121 @@ class DeviceEnvPipeline:
         return self.agent_sensor(scaled), rewards, terminated, truncated, infos
 
     def rollout(self, select_action: Callable[[torch.Tensor], torch.Tensor], num_steps: int,
-                last_obs: Optional[torch.Tensor] = None, seed: Optional[int] = None):
+                last_obs: Optional[torch.Tensor] = None, seed: Optional[int] = None, reuse_buffers: bool = False):
         """Batched ``Worker.rollout`` (worker.py:39-93): ``num_steps`` env steps with a GPU-resident
         ``select_action(scaled_obs) -> actions in [-1,1]``; returns ``(RolloutBatch, last_obs)`` with all
-        tensors on the device.  No host synchronisation inside the loop."""
+        tensors on the device.  No host synchronisation inside the loop: the transitions are written
+        into ``[T, B, ...]`` buffers allocated up front.  ``reuse_buffers=True`` keeps those buffers
+        for the next rollout of the same length (the returned batch is then overwritten by it --
+        copy what must survive, e.g. into the replay), which removes every allocation from the loop."""
         if last_obs is None:
             last_obs = self.reset(seed=seed)
-        last_stored = self.obs_store[self.obs_mask].reshape(self.B, -1, *self.obs_store.shape[2:]).clone()
-        rec = {k: [] for k in RolloutBatch._fields}
-        for _ in range(num_steps):
+        last_stored = self._valid(self.obs_store, self._obs_row)
+        S, dev = last_stored.shape[1], last_stored.device
+        key = (num_steps, S)
+        buf = self._rollout_buf.get(key) if reuse_buffers else None
+        if buf is None:
+            lead = (num_steps, self.B)
+            buf = RolloutBatch(
+                obs=torch.empty(lead + tuple(last_stored.shape[1:]), dtype=last_stored.dtype, device=dev),
+                actions=torch.empty(lead + (S, 1, self.env.J), dtype=torch.float32, device=dev),
+                nxtobs=torch.empty(lead + tuple(last_stored.shape[1:]), dtype=last_stored.dtype, device=dev),
+                rewards=torch.empty(lead, dtype=torch.float64, device=dev),
+                terminated=torch.zeros(lead, dtype=torch.bool, device=dev),
+                truncated=torch.empty(lead, dtype=torch.bool, device=dev),
+                steps=torch.empty(lead, dtype=torch.int64, device=dev))
+            if reuse_buffers:
+                self._rollout_buf = {key: buf}
+        for t in range(num_steps):
             with torch.no_grad():
                 actions = select_action(last_obs)
             last_obs, rewards, terminated, truncated, infos = self.step(actions)
-            obs = last_stored
-            last_stored = self.obs_store[self.obs_mask].reshape(self.B, -1, *self.obs_store.shape[2:]).clone()
-            nxtobs = last_stored.clone()
-            stored_actions = self.act_store[self.act_mask].reshape(self.B, -1, 1, self.env.J).clone()
-            if "final_observation" in infos:
-                idx = infos["_final_observation"]
-                nxtobs[idx] = self.finals[idx][:, -obs.shape[1]:]
-            for k, v in zip(RolloutBatch._fields, (obs, stored_actions, nxtobs, rewards, terminated, truncated,
-                                                   infos["step"])):
-                rec[k].append(v)
-        return RolloutBatch(*(torch.stack(rec[k]) for k in RolloutBatch._fields)), last_obs
+            buf.obs[t].copy_(last_stored)
+            last_stored = self._valid(self.obs_store, self._obs_row)
+            buf.actions[t].copy_(self._valid(self.act_store, self._act_row))
+            if "final_observation" in infos:                        # every env of the batch at once
+                buf.nxtobs[t].copy_(self.finals[:, -S:])
+            else:
+                buf.nxtobs[t].copy_(last_stored)
+            buf.rewards[t].copy_(rewards)
+            buf.truncated[t].copy_(truncated)
+            buf.steps[t].copy_(infos["step"])
+        return buf, last_obs
+
+    # -- CUDA-graph rollout ----------------------------------------------------------------------
+    def rollout_graphed(self, select_action: Callable[[torch.Tensor], torch.Tensor], num_steps: int,
+                        last_obs: Optional[torch.Tensor] = None, seed: Optional[int] = None):
+        """``rollout`` with the whole step -- policy forward, action scaling, the env kernel, store /
+        scaling bookkeeping and the writes into the transition buffers -- captured ONCE in a CUDA
+        graph and replayed per step (one graph launch instead of ~40 small kernel launches; the
+        loop is launch-bound, above all with the spectral solver whose period kernel takes 30 us).
+        Requirements: ``num_steps`` of the stores = 1 (the reference's MBRL loop), a ``select_action``
+        made of capturable torch ops with fixed shapes, CUDA tensors.  The step on which the episode
+        ends (auto-reset, burn-in launch with a fresh seed) runs eagerly on the same in-place state.
+        Returns ``(RolloutBatch, last_obs)``; the batch lives in buffers that the next graphed
+        rollout of the same length overwrites."""
+        if self.num_steps != 1:
+            raise ValueError("rollout_graphed needs num_steps == 1")
+        if last_obs is None:
+            last_obs = self.reset(seed=seed)
+        dev = last_obs.device
+        key = (id(select_action), num_steps)
+        g = self._graphs.get(key)
+        if g is None:
+            lead = (num_steps, self.B)
+            st = self.obs_store
+            buf = RolloutBatch(
+                obs=torch.empty(lead + tuple(st.shape[1:]), dtype=st.dtype, device=dev),
+                actions=torch.empty(lead + (1, 1, self.env.J), dtype=torch.float32, device=dev),
+                nxtobs=torch.empty(lead + tuple(st.shape[1:]), dtype=st.dtype, device=dev),
+                rewards=torch.empty(lead, dtype=torch.float64, device=dev),
+                terminated=torch.zeros(lead, dtype=torch.bool, device=dev),
+                truncated=torch.empty(lead, dtype=torch.bool, device=dev),
+                steps=torch.empty(lead, dtype=torch.int64, device=dev))
+            g = dict(buf=buf, obs_in=last_obs.clone(), t=torch.zeros(1, dtype=torch.int64, device=dev), graph=None,
+                     store=self.obs_store)
+            self._graphs = {key: g}
+        if g["store"] is not self.obs_store:         # an explicit reset() re-created the stores
+            g["graph"], g["store"] = None, self.obs_store
+        buf, obs_in, t_idx = g["buf"], g["obs_in"], g["t"]
+        obs_in.copy_(last_obs)
+        t_idx.zero_()
+
+        def one_step():
+            with torch.no_grad():
+                actions = select_action(obs_in)
+            buf.obs.index_copy_(0, t_idx, self.obs_store.unsqueeze(0))          # stored obs before the step
+            new_obs, rewards, terminated, truncated, infos = self.step(actions)
+            buf.actions.index_copy_(0, t_idx, self.act_store.unsqueeze(0))
+            nxt = self.finals if "final_observation" in infos else self.obs_store
+            buf.nxtobs.index_copy_(0, t_idx, nxt.unsqueeze(0))
+            buf.rewards.index_copy_(0, t_idx, rewards.unsqueeze(0))
+            buf.truncated.index_copy_(0, t_idx, truncated.unsqueeze(0))
+            buf.steps.index_copy_(0, t_idx, infos["step"].unsqueeze(0))
+            obs_in.copy_(new_obs)
+            t_idx.add_(1)
+
+        for _ in range(num_steps):
+            if self._episode_step + 1 >= self.env.max_episode_steps:
+                one_step()                           # episode end: eager (auto-reset inside step())
+                continue
+            if g["graph"] is None:
+                # one real step on a side stream as warm-up (library handles, allocator), then -- unless
+                # the next step ends the episode -- the capture; a capture executes nothing, so exactly
+                # one transition is produced in this iteration
+                side = torch.cuda.Stream(device=dev)
+                side.wait_stream(torch.cuda.current_stream(dev))
+                with torch.cuda.stream(side):
+                    one_step()
+                torch.cuda.current_stream(dev).wait_stream(side)
+                if self._episode_step + 1 < self.env.max_episode_steps:
+                    graph = torch.cuda.CUDAGraph()
+                    host_count = self._episode_step
+                    with torch.cuda.graph(graph):
+                        one_step()
+                    self._episode_step = host_count      # undo the capture's host-side bookkeeping
+                    g["graph"] = graph
+                continue
+            g["graph"].replay()
+            self._episode_step += 1
+        return buf, obs_in.clone()
