@@ -50,7 +50,8 @@ enum ks_where { KS_HOST = 0, KS_DEVICE = 1 };
  *   in-register / warp-level FFT.  NOT in the reference: it integrates the same equation
  *   (kuramoto.py:127) with a different discretisation, `dt` and `cfg_steps` are then the ETDRK4
  *   step and the steps per control period (e.g. dt = 0.025, cfg_steps = 10 for the reference's
- *   0.25 time units).  N = 64, 128 or 256 and KS_REWARD_L2 only. */
+ *   0.25 time units).  N = 64, 128 or 256.  KS_REWARD_DISSIPATION uses spectral derivatives
+ *   (uxx of u, and -- literally as kuramoto.py:67-70,120-122 -- the derivative of u^2 for "ux"). */
 enum ks_solver { KS_SOLVER_FD_RK4 = 0, KS_SOLVER_ETDRK4 = 1 };
 
 enum ks_error {

@@ -116,7 +116,7 @@ void fill_coef(ks::Coef<T> &c, double dx, double dt)
 //   closed forms near L = 0);  g = -k/2 * dealias multiplies i*FFT(u^2).
 // The kernel carries the nonlinear terms pre-multiplied by Q, so the tables it gets are
 //   E, E2, f1/Q, 2 f2/Q, f3/Q, Q g / N, Q / N   (ks::kTabE ... kTabQN; the 1/N makes the kernel's
-//   unnormalised transform pair an identity).
+//   unnormalised transform pair an identity), and for the dissipation reward -k^2 and k / N.
 void etd_tables_host(int N, double L, double h, bool dealias, std::vector<double> &out)
 {
     constexpr int M = 32;
@@ -145,6 +145,8 @@ void etd_tables_host(int N, double L, double h, bool dealias, std::vector<double
         out[(size_t)ks::kTabR3 * N + i] = f3 / Q;
         out[(size_t)ks::kTabG * N + i] = keep ? Q * (-0.5 * k_odd) / N : 0.0;
         out[(size_t)ks::kTabQN * N + i] = Q / N;
+        out[(size_t)ks::kTabK2 * N + i] = -k2;
+        out[(size_t)ks::kTabKN * N + i] = k_odd / N;
     }
 }
 
@@ -386,9 +388,8 @@ int ks_create(const ks_config *cfg, ks_handle **out)
     if (cfg->solver != KS_SOLVER_FD_RK4 && cfg->solver != KS_SOLVER_ETDRK4)
         return fail(nullptr, KS_ERR_ARG, "ks_create: bad solver %d", cfg->solver);
     const bool etd = cfg->solver == KS_SOLVER_ETDRK4;
-    if (etd && ((cfg->N != 64 && cfg->N != 128 && cfg->N != 256) || cfg->reward_mode != KS_REWARD_L2))
-        return fail(nullptr, KS_ERR_UNSUPPORTED, "ks_create: the spectral ETDRK4 solver supports N = 64, 128, 256 and the L2 "
-                    "reward only (N=%d reward_mode=%d)", cfg->N, cfg->reward_mode);
+    if (etd && cfg->N != 64 && cfg->N != 128 && cfg->N != 256)
+        return fail(nullptr, KS_ERR_UNSUPPORTED, "ks_create: the spectral ETDRK4 solver supports N = 64, 128, 256 (N=%d)", cfg->N);
 
     int P = etd ? 8 : cfg->points_per_lane;
     if (P != 0 && (P < ks::kMinP || P > ks::kMaxP || cfg->N % P || cfg->N / P > 32))
@@ -436,7 +437,7 @@ int ks_create(const ks_config *cfg, ks_handle **out)
         h->envs_per_warp = 8 / R;
         const int per_cta = h->envs_per_warp * (ks::kBlockThreads / 32);
         h->grid = (int)((cfg->num_envs + per_cta - 1) / per_cta);
-        h->kernel = f64 ? ks::etd_kernel_f64(R) : ks::etd_kernel_f32(R);
+        h->kernel = f64 ? ks::etd_kernel_f64(R, cfg->reward_mode) : ks::etd_kernel_f32(R, cfg->reward_mode);
     }
     const double dx = cfg->L / cfg->N;  // kuramoto.py:55
     fill_coef(h->c64, dx, cfg->dt);

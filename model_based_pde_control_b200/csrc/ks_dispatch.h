@@ -13,9 +13,9 @@ const void *period_kernel_f64_l2(int P);
 const void *period_kernel_f64_diss(int P);
 const void *period_kernel_f32_l2(int P);
 const void *period_kernel_f32_diss(int P);
-// Spectral ETDRK4 solver (ks_etd.cuh, N = 64 R): one kernel per precision and R in {1, 2, 4}.
-const void *etd_kernel_f64(int R);
-const void *etd_kernel_f32(int R);
+// Spectral ETDRK4 solver (ks_etd.cuh, N = 64 R): one kernel per precision, R in {1, 2, 4} and reward mode.
+const void *etd_kernel_f64(int R, int reward_mode);
+const void *etd_kernel_f32(int R, int reward_mode);
 
 }  // namespace ks
 

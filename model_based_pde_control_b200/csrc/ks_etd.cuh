@@ -40,9 +40,9 @@ constexpr int kEtdN = 64;          // grid points of the base layout; the kernel
 // Per-wavenumber tables, each [N] in natural FFT order (host-precomputed, ks_api.cu).  The kernel
 // carries the nonlinear terms pre-multiplied by Q (N~ = Q N), which removes Q from the stage
 // formulas; the final combination then needs f1/Q, 2 f2/Q, f3/Q (Q = h phi_1(hL/2)/2 > 0).
-constexpr int kEtdTables = 7;
+constexpr int kEtdTables = 9;
 enum { kTabE = 0, kTabE2, kTabR1 /* f1/Q */, kTabR22 /* 2 f2/Q */, kTabR3 /* f3/Q */, kTabG /* Q g / N */,
-       kTabQN /* Q / N */ };
+       kTabQN /* Q / N */, kTabK2 /* -k^2 (even-derivative k) */, kTabKN /* k / N (odd-derivative k) */ };
 
 template <typename T>
 struct __align__(2 * sizeof(T)) C2 {
@@ -225,21 +225,61 @@ __device__ __forceinline__ C2<T> tab2(const C2<T> *tab, int which, int h, int pl
 // Spectral right-hand side without the linear part, pre-multiplied by Q, in place:
 //   w <- i (Q g / N) * FFT( (Re/Im IFFT(w))^2 ) + Q phi_hat / N        (both packed fields at once)
 // With FIRST the squares of the physical values are the pre-step reward terms (kuramoto.py:84).
-template <typename T, int R, bool FIRST>
+template <typename T>
+__device__ __forceinline__ T sum8(const T (&a)[8])
+{
+    return ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
+}
+
+// Reward terms of the pre-step state, per lane partial sums for the two envs of the pair:
+//   L2 mode:           a = sum u^2                                      (kuramoto.py:64-65)
+//   dissipation mode:  a = sum uxx^2,  b = sum ux^2,  c = sum u*phi     (kuramoto.py:67-70), where
+//     -- literally as in the reference -- ux is the derivative of u^2 (rhs() differentiates u**2,
+//     kuramoto.py:120-122); both derivatives are spectral here.
+template <typename T>
+struct EtdReward {
+    T a[2], b[2], c[2];
+};
+
+template <typename T, int R, bool FIRST, int RMODE>
 __device__ __forceinline__ void nonlinear(T (&wx)[8], T (&wy)[8], const FftCtx<T> &ctx, const C2<T> *tab,
-                                          const T (&phx)[8], const T (&phy)[8], int pl, T &racc_a, T &racc_b)
+                                          const T (&phx)[8], const T (&phy)[8], int pl, EtdReward<T> &rw,
+                                          const float (&pfx)[8], const float (&pfy)[8])
 {
     ifft64<T, R>(wx, wy, ctx);
+    if constexpr (FIRST && RMODE == kRewardDissipation) {
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {          // power term u * phi with the float32 jets
+            rw.c[0] = fma_t<T>(wx[r], T(pfx[r]), rw.c[0]);
+            rw.c[1] = fma_t<T>(wy[r], T(pfy[r]), rw.c[1]);
+        }
+    }
 #pragma unroll
     for (int r = 0; r < 8; ++r) {
         wx[r] = wx[r] * wx[r];
         wy[r] = wy[r] * wy[r];
     }
-    if constexpr (FIRST) {
-        racc_a += ((wx[0] + wx[1]) + (wx[2] + wx[3])) + ((wx[4] + wx[5]) + (wx[6] + wx[7]));
-        racc_b += ((wy[0] + wy[1]) + (wy[2] + wy[3])) + ((wy[4] + wy[5]) + (wy[6] + wy[7]));
+    if constexpr (FIRST && RMODE == kRewardL2) {
+        rw.a[0] += sum8<T>(wx);
+        rw.a[1] += sum8<T>(wy);
     }
     fft64<T, R>(wx, wy, ctx);
+    if constexpr (FIRST && RMODE == kRewardDissipation) {
+        // (u^2)_x = IFFT(i k FFT(u^2)) / N for both fields at once
+        T dx[8], dy[8];
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+            const C2<T> kn = tab2<T, 8 * R>(tab, kTabKN, h, pl);
+            dx[2 * h] = -kn.x * wy[2 * h];         dy[2 * h] = kn.x * wx[2 * h];
+            dx[2 * h + 1] = -kn.y * wy[2 * h + 1]; dy[2 * h + 1] = kn.y * wx[2 * h + 1];
+        }
+        ifft64<T, R>(dx, dy, ctx);
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            rw.b[0] = fma_t<T>(dx[r], dx[r], rw.b[0]);
+            rw.b[1] = fma_t<T>(dy[r], dy[r], rw.b[1]);
+        }
+    }
 #pragma unroll
     for (int h = 0; h < 4; ++h) {
         const C2<T> g = tab2<T, 8 * R>(tab, kTabG, h, pl);
@@ -259,7 +299,7 @@ struct EtdParams {
 // ---------------------------------------------------------------------------------------------
 // The spectral control-period kernel: K periods x cfg_steps ETDRK4 steps, 8/R envs per warp.
 // ---------------------------------------------------------------------------------------------
-template <typename T, int R>
+template <typename T, int R, int RMODE>
 __global__ void __launch_bounds__(kBlockThreads) ks_etd_kernel(const EtdParams ep)
 {
     static_assert(R == 1 || R == 2 || R == 4, "N = 64 R with R = 1, 2, 4");
@@ -335,6 +375,7 @@ __global__ void __launch_bounds__(kBlockThreads) ks_etd_kernel(const EtdParams e
     for (int k = 0; k < p.K; ++k) {
         // ---- jet forcing of this period: float32 FMA chain (transforms.py:262-265), then its spectrum
         T phx[8], phy[8];      // Q phi_hat / N, kept in registers for the whole period
+        [[maybe_unused]] float pfx[8], pfy[8];     // the jets in physical space (dissipation reward: u * phi)
         {
             T (&fx)[8] = phx, (&fy)[8] = phy;
             if (p.phi != nullptr) {
@@ -367,6 +408,8 @@ __global__ void __launch_bounds__(kBlockThreads) ks_etd_kernel(const EtdParams e
 #pragma unroll
                 for (int r = 0; r < 8; ++r) fx[r] = fy[r] = T(0);
             }
+#pragma unroll
+            for (int r = 0; r < 8; ++r) { pfx[r] = (float)fx[r]; pfy[r] = (float)fy[r]; }
             fft64<T, R>(fx, fy, ctx);
 #pragma unroll
             for (int h = 0; h < 4; ++h) {
@@ -389,13 +432,28 @@ __global__ void __launch_bounds__(kBlockThreads) ks_etd_kernel(const EtdParams e
         // ---- cfg_steps ETDRK4 steps (Cox & Matthews 2002, eqs. 26-29), with N~ = Q N:
         //   a = E2 v + N~v          b = E2 v + N~a = (a - N~v) + N~a          c = E2 a + 2 N~b - N~v
         //   v' = E v + (f1/Q) N~v + (2 f2/Q) (N~a + N~b) + (f3/Q) N~c
-        T racc_a = T(0), racc_b = T(0), dummy = T(0);
+        EtdReward<T> rw{{T(0), T(0)}, {T(0), T(0)}, {T(0), T(0)}};
         for (int s = 0; s < p.cfg_steps; ++s) {
             T nx[8], ny[8], ax[8], ay[8], wx[8], wy[8];
+            if constexpr (RMODE == kRewardDissipation) {
+                // uxx = IFFT(-k^2 v) of the pre-step state, both fields at once
+#pragma unroll
+                for (int h = 0; h < 4; ++h) {
+                    const C2<T> k2 = tab2<T, LP>(tab, kTabK2, h, pl);
+                    wx[2 * h] = k2.x * vx[2 * h];         wy[2 * h] = k2.x * vy[2 * h];
+                    wx[2 * h + 1] = k2.y * vx[2 * h + 1]; wy[2 * h + 1] = k2.y * vy[2 * h + 1];
+                }
+                ifft64<T, R>(wx, wy, ctx);
+#pragma unroll
+                for (int r = 0; r < 8; ++r) {
+                    rw.a[0] = fma_t<T>(wx[r], wx[r], rw.a[0]);
+                    rw.a[1] = fma_t<T>(wy[r], wy[r], rw.a[1]);
+                }
+            }
             // N~v
 #pragma unroll
             for (int m = 0; m < 8; ++m) { nx[m] = vx[m]; ny[m] = vy[m]; }
-            nonlinear<T, R, true>(nx, ny, ctx, tab, phx, phy, pl, racc_a, racc_b);
+            nonlinear<T, R, true, RMODE>(nx, ny, ctx, tab, phx, phy, pl, rw, pfx, pfy);
             // a = E2 v + N~v
 #pragma unroll
             for (int h = 0; h < 4; ++h) {
@@ -409,7 +467,7 @@ __global__ void __launch_bounds__(kBlockThreads) ks_etd_kernel(const EtdParams e
                 }
             }
             // N~a
-            nonlinear<T, R, false>(wx, wy, ctx, tab, phx, phy, pl, dummy, dummy);
+            nonlinear<T, R, false, RMODE>(wx, wy, ctx, tab, phx, phy, pl, rw, pfx, pfy);
             // b = (a - N~v) + N~a (-> w);   a <- E2 a - N~v;   v <- E v + (f1/Q) N~v + (2 f2/Q) N~a
 #pragma unroll
             for (int h = 0; h < 4; ++h) {
@@ -429,7 +487,7 @@ __global__ void __launch_bounds__(kBlockThreads) ks_etd_kernel(const EtdParams e
                 }
             }
             // N~b
-            nonlinear<T, R, false>(wx, wy, ctx, tab, phx, phy, pl, dummy, dummy);
+            nonlinear<T, R, false, RMODE>(wx, wy, ctx, tab, phx, phy, pl, rw, pfx, pfy);
             // v += (2 f2/Q) N~b;   c = (E2 a - N~v) + 2 N~b (-> w)
 #pragma unroll
             for (int h = 0; h < 4; ++h) {
@@ -445,7 +503,7 @@ __global__ void __launch_bounds__(kBlockThreads) ks_etd_kernel(const EtdParams e
                 }
             }
             // N~c;   v += (f3/Q) N~c
-            nonlinear<T, R, false>(wx, wy, ctx, tab, phx, phy, pl, dummy, dummy);
+            nonlinear<T, R, false, RMODE>(wx, wy, ctx, tab, phx, phy, pl, rw, pfx, pfy);
 #pragma unroll
             for (int h = 0; h < 4; ++h) {
                 const C2<T> r3 = tab2<T, LP>(tab, kTabR3, h, pl);
@@ -462,7 +520,8 @@ __global__ void __launch_bounds__(kBlockThreads) ks_etd_kernel(const EtdParams e
         ifft64<T, R>(ux, uy, ctx);
 
         // ---- period epilogue: reward, flags, observation (kuramoto.py:92-98)
-        double ra = (double)racc_a, rb = (double)racc_b;
+        double ra = (double)rw.a[0] + (double)rw.b[0] + (double)rw.c[0];
+        double rb = (double)rw.a[1] + (double)rw.b[1] + (double)rw.c[1];
         bool bA = false, bB = false;
 #pragma unroll
         for (int r = 0; r < 8; ++r) {

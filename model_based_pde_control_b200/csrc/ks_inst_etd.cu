@@ -1,23 +1,21 @@
 // Instantiations of the spectral ETDRK4 control-period kernel (ks_etd.cuh): T = double / float,
-// N = 64 R with R = 1, 2, 4.
+// N = 64 R with R = 1, 2, 4, both reward modes.
 #include "ks_dispatch.h"
 #include "ks_etd.cuh"
 
-const void *ks::etd_kernel_f64(int R)
-{
-    switch (R) {
-        case 1: return (const void *)&ks::ks_etd_kernel<double, 1>;
-        case 2: return (const void *)&ks::ks_etd_kernel<double, 2>;
-        case 4: return (const void *)&ks::ks_etd_kernel<double, 4>;
-        default: return nullptr;
+#define KS_ETD_LOOKUP(NAME, T)                                                                        \
+    const void *ks::NAME(int R, int rmode)                                                            \
+    {                                                                                                 \
+        const bool l2 = rmode == ks::kRewardL2;                                                       \
+        switch (R) {                                                                                  \
+            case 1: return l2 ? (const void *)&ks::ks_etd_kernel<T, 1, ks::kRewardL2>                 \
+                              : (const void *)&ks::ks_etd_kernel<T, 1, ks::kRewardDissipation>;       \
+            case 2: return l2 ? (const void *)&ks::ks_etd_kernel<T, 2, ks::kRewardL2>                 \
+                              : (const void *)&ks::ks_etd_kernel<T, 2, ks::kRewardDissipation>;       \
+            case 4: return l2 ? (const void *)&ks::ks_etd_kernel<T, 4, ks::kRewardL2>                 \
+                              : (const void *)&ks::ks_etd_kernel<T, 4, ks::kRewardDissipation>;       \
+            default: return nullptr;                                                                  \
+        }                                                                                             \
     }
-}
-const void *ks::etd_kernel_f32(int R)
-{
-    switch (R) {
-        case 1: return (const void *)&ks::ks_etd_kernel<float, 1>;
-        case 2: return (const void *)&ks::ks_etd_kernel<float, 2>;
-        case 4: return (const void *)&ks::ks_etd_kernel<float, 4>;
-        default: return nullptr;
-    }
-}
+KS_ETD_LOOKUP(etd_kernel_f64, double)
+KS_ETD_LOOKUP(etd_kernel_f32, float)

@@ -21,8 +21,8 @@ through the long-horizon statistics fixture (``tests/golden/stats_*.npz``).
 Everything that is *not* the time stepper is shared with the reference path and follows it:
   jet forcing phi = a @ F in float32          pdegym/common/transforms.py:250-265
   reward = mean over sub-steps of -mean(u^2) of the PRE-step state   kuramoto.py:64-65,82-84,96
-  (dissipation mode: -(mean(uxx^2) + mean(ux^2) + mean(u phi)) with spectral derivatives --
-   here ux is du/dx, the README's meaning, not the reference's upwind d(u^2)/dx)
+  (dissipation mode: -(mean(uxx^2) + mean(ux^2) + mean(u phi)) with spectral derivatives; as in
+   the reference's code "ux" is the derivative of u^2, kuramoto.py:67-70,120-122)
   timestep / truncation / observation cast                            kuramoto.py:92-98
 """
 from __future__ import annotations
@@ -39,6 +39,7 @@ class ETDCoefficients:
     """Per-wavenumber tables, natural FFT order (``np.fft.fftfreq`` order), all real."""
 
     k: np.ndarray        # wavenumbers for odd derivatives (Nyquist entry zeroed)
+    k_even: np.ndarray   # wavenumbers for even derivatives (Nyquist keeps |k|)
     lin: np.ndarray      # L(k) = k^2 - k^4 (Nyquist entry uses |k| = pi N / L)
     E: np.ndarray        # exp(h L)
     E2: np.ndarray       # exp(h L / 2)
@@ -72,7 +73,7 @@ def etd_coefficients(N: int, L: float, h: float, dealias: bool = True, M: int = 
     else:
         mask = np.ones(N)
     g = -0.5 * k_odd * mask
-    return ETDCoefficients(k=k_odd, lin=lin, E=E, E2=E2, Q=Q, f1=f1, f2=f2, f3=f3, g=g, mask=mask, h=h)
+    return ETDCoefficients(k=k_odd, k_even=k_even, lin=lin, E=E, E2=E2, Q=Q, f1=f1, f2=f2, f3=f3, g=g, mask=mask, h=h)
 
 
 def nonlinear(v: np.ndarray, c: ETDCoefficients, phi_hat: np.ndarray):
@@ -98,14 +99,11 @@ def substep_reward(u: np.ndarray, v: np.ndarray, phi: np.ndarray, c: ETDCoeffici
     """Per-sub-step reward of the pre-step state (kuramoto.py:64-70), batched over leading dims."""
     if reward_mode == "l2":
         return -np.mean(u * u, axis=-1)
-    # dissipation + power with spectral derivatives (Parseval: mean(f^2) = sum |f_hat|^2 / N^2)
-    N = u.shape[-1]
-    p = np.abs(v) ** 2 / (N * N)
-    k2 = c.k ** 2
-    k2_even = np.where(c.lin != 0, (1.0 + np.sqrt(np.maximum(1.0 - 4.0 * c.lin, 0.0))) / 2.0, 0.0)  # k^2 from k^2-k^4
-    uxx2 = np.sum(k2_even ** 2 * p, axis=-1)
-    ux2 = np.sum(k2 * p, axis=-1)
-    return -(uxx2 + ux2 + np.mean(u * phi, axis=-1))
+    # kuramoto.py:67-70 with spectral derivatives.  Literally as the reference: rhs() differentiates
+    # u**2 (kuramoto.py:120-122), so "ux" is the derivative of u^2 (not dealiased), uxx that of u.
+    ux = np.real(np.fft.ifft(1j * c.k * np.fft.fft(u * u, axis=-1), axis=-1))
+    uxx = np.real(np.fft.ifft(-(c.k_even ** 2) * v, axis=-1))
+    return -(np.mean(uxx * uxx, axis=-1) + np.mean(ux * ux, axis=-1) + np.mean(u * phi, axis=-1))
 
 
 def step(u0: np.ndarray, phi: np.ndarray, N: int, L: float, dt: float, cfg_steps: int, reward_mode: str = "l2",

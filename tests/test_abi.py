@@ -59,7 +59,6 @@ def good_config(**kw):
     (dict(N=1024), _lib.KS_ERR_UNSUPPORTED),          # would need more than one warp per env
     (dict(solver=3), _lib.KS_ERR_ARG),
     (dict(solver=1, N=96), _lib.KS_ERR_UNSUPPORTED),       # spectral solver: N = 64, 128, 256 only
-    (dict(solver=1, reward_mode=1), _lib.KS_ERR_UNSUPPORTED),
 ])
 def test_create_rejects_bad_config_without_a_device(bad, code):
     lib = _lib.load()

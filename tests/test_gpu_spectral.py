@@ -99,6 +99,33 @@ def test_larger_grids_vs_oracle(N, L, J, B, precision):
     env.close()
 
 
+@pytest.mark.parametrize("N,L,J,B", [(64, 22.0, 4, 21), (256, 88.0, 8, 6)])
+def test_dissipation_reward_mode(N, L, J, B):
+    """reward_mode="dissipation": -(mean uxx^2 + mean ux^2 + mean u*phi) per sub-step with spectral
+    derivatives (two extra inverse transforms per ETDRK4 step), "ux" = d(u^2)/dx as in kuramoto.py:67-70."""
+    from model_based_pde_control_b200 import KSVecEnv
+    from oracle import ks_etdrk4 as ke, ks_numpy as ko
+
+    rng = np.random.default_rng(N)
+    env = KSVecEnv(B, dict(N=N, L=L, dt=DT, cfg_steps=S), Xi=[k / J for k in range(J)], solver="etdrk4",
+                   reward_mode="dissipation")
+    u0 = np.concatenate([smooth_states(rng, B, 64)] * (N // 64), axis=1) * 0.7 + rng.uniform(-0.1, 0.1, (B, N))
+    a = rng.uniform(-1, 1, (B, 1, J)).astype(np.float32)
+    env.set_state(u0, 0)
+    _, rew, *_ = env.step(a)
+    u1, _ = env.get_state()
+    phi = ko.forcing(a.reshape(B, J), env.forcing.matrix())
+    u_ref, r_ref = ke.step(u0, phi, N, L, DT, S, reward_mode="dissipation")
+    assert rel_l2(u1, u_ref).max() <= TOL64
+    assert np.abs((rew - r_ref) / r_ref).max() <= TOL64, np.abs((rew - r_ref) / r_ref).max()
+    # the state does not depend on the reward mode (two kernel instantiations: equal up to rounding)
+    env2 = KSVecEnv(B, dict(N=N, L=L, dt=DT, cfg_steps=S), Xi=[k / J for k in range(J)], solver="etdrk4")
+    env2.set_state(u0, 0)
+    _, rew_l2, *_ = env2.step(a)
+    assert rel_l2(env2.get_state()[0], u1).max() < 1e-13 and not np.allclose(rew_l2, rew)
+    env.close(); env2.close()
+
+
 def test_rough_initial_condition_and_no_dealias():
     """White-noise states (every mode excited, as the reset's U(-0.4,0.4) draw) with and without the 2/3 rule."""
     rng = np.random.default_rng(5)
