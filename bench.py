@@ -104,6 +104,11 @@ def cpu_c_port_throughput(envs: int = 64, periods: int = 4):
     return envs * periods / dt, ks_c.num_threads()
 
 
+def workload_name(B, world, N, L, J, S, dt, precision):
+    return (f"{B} KS envs per GPU x {world} GPU(s) = {B * world} envs, N={N} L={L} J={J}, cfg_steps={S} RK4 sub-steps "
+            f"per control period, dt={dt}, {precision}, random actions (BASELINE.json configs[1] per GPU)")
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -117,8 +122,9 @@ def run_reference_arm(args):
         "impl": "reference", "metric": METRIC, "value": thr, "unit": UNIT, "n_gpus": args.gpus,
         "steps": per_proc, "warmup": min(warm, 2), "ms_per_step": 1e3 * procs / thr,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "KuramotoSivashinskyEnv-v0 step, default grid N=64 L=22 J=4, cfg_steps=250, "
-                               "random actions; one env per host core (the reference's process-per-env parallelism)"},
+        "config": {"workload": workload_name(args.envs_per_gpu, max(1, args.gpus), 64, 22.0, 4, 250, 0.001, "f64"),
+                   "sample": f"bounded sample of that workload: {procs} of its envs, one per host core (the reference's "
+                             f"process-per-env parallelism, mbrl.py:81-86), {per_proc} control periods each"},
         "cpu_baseline": {"value": thr, "unit": UNIT, "cores": procs, "kind": "port",
                          "sample": f"{procs} processes x {per_proc} control periods of 1 env each, NumPy/SciPy port "
                                    "of the reference step (scipy.ndimage.convolve1d stencils, per-sub-step reward)"},
@@ -383,9 +389,7 @@ def run_gpu_arm(args):
         "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": args.precision, "data": "synthetic",
         "config": {
-            "workload": f"{B} KS envs per GPU x {world} GPU(s) = {total_envs} envs, N={N} L={env.L} J={J}, "
-                        f"cfg_steps={S} RK4 sub-steps per control period, dt={env.dt}, {args.precision}, "
-                        "random actions (BASELINE.json configs[1] per GPU)",
+            "workload": workload_name(B, world, N, env.L, J, S, env.dt, args.precision),
             "envs_per_gpu": B, "total_envs": total_envs, "N": N, "J": J, "cfg_steps": S,
             "l2": "flushed (256 MiB memset) between timed steps, outside the per-step event pairs"
                   + ("; ranks re-aligned after each flush by a 4-byte all-reduce, also outside the pairs" if world > 1 else ""),
