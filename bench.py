@@ -14,7 +14,8 @@ Timed regions
 * ``value``: K x ``ks_step`` with actions already resident in HBM, CUDA events around every
   step on the launching stream, L2 flushed between timed steps, max over ranks.
 * ``e2e``: K x ``KSVecEnv.step(numpy actions)`` -- the call a user of the gym API makes -- host
-  buffers, H2D + kernel + D2H + sync inside the region (wall clock around synchronous calls).
+  buffers in, host buffers out, synchronised every step (wall clock around synchronous calls); the
+  host->device and device->host traffic happens inside the kernel (zero-copy over PCIe).
 * ``cpu_baseline`` / ``--impl reference``: the oracle's NumPy/SciPy port of the reference's
   ``step`` (same third-party calls the reference makes) on every host core.
 """
@@ -402,7 +403,8 @@ def run_gpu_arm(args):
         },
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": env.h2d_bytes_per_step,
                 "d2h_bytes_per_step": env.d2h_bytes_per_step, "ms_per_step": 1e3 * e2e_s / K,
-                "api": "KSVecEnv.step(numpy actions) -> ks_step_host (pinned H2D, kernel, packed D2H, sync)"},
+                "api": "KSVecEnv.step(numpy actions) -> ks_step_host: one launch + sync; the kernel reads the pinned actions over PCIe "
+                       "and mirrors the packed outputs into the pinned host block (KS_HOST_IO=copy: H2D copy, kernel, D2H copy)"},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {

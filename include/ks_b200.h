@@ -131,8 +131,12 @@ int ks_rollout(ks_handle *h, int32_t K, const float *actions, float *obs, double
                uint8_t *truncated, int32_t *step, uint8_t *nonfinite, void *stream);
 
 /* Host-buffer form of ks_step -- the call the gym-facing wrapper makes when the policy lives on
- * the host (worker.py:60-66): copies actions host->device, runs the period, copies ONE packed
- * output block device->host and synchronises.  Layout of the block (see ks_out_layout):
+ * the host (worker.py:60-66).  With pinned (device-addressable) buffers the step is ONE launch and a
+ * synchronise: the kernel reads the actions straight from host memory and its epilogue mirrors
+ * every output into the host block over PCIe (the mirrored-store path of the multi-GPU exchange).
+ * With pageable buffers, or KS_HOST_IO=copy in the environment, it copies actions host->device,
+ * runs the period and copies ONE packed output block device->host.  Either way it synchronises
+ * `stream` before returning.  Layout of the block (see ks_out_layout):
  *   reward f64 [B] | obs f32 [B*No] | step i32 [B] | truncated u8 [B] | nonfinite u8 [B]
  * (each part 16-byte aligned). */
 int ks_step_host(ks_handle *h, const float *actions_host, void *out_host, void *stream);

@@ -7,6 +7,7 @@
 #include <complex>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -658,15 +659,43 @@ int ks_rollout(ks_handle *h, int32_t K, const float *actions, float *obs, double
     return launch_period(h, K, actions, nullptr, obs, reward, truncated, step, nonfinite, 0, nullptr, (cudaStream_t)stream);
 }
 
+namespace {
+// Is `p` pinned host memory that kernels of the current device can address as it is (UVA)?
+bool device_addressable_host(const void *p)
+{
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeHost && a.devicePointer == p;
+}
+}  // namespace
+
 int ks_step_host(ks_handle *h, const float *actions_host, void *out_host, void *stream_)
 {
     if (!h || !actions_host || !out_host) return h ? fail(h, KS_ERR_ARG, "ks_step_host: NULL argument") : KS_ERR_ARG;
     cudaStream_t stream = (cudaStream_t)stream_;
     DeviceGuard guard(h->cfg.device);
     const size_t B = h->cfg.num_envs;
+    float *obs = (float *)(h->out + h->out_off[1]);
+    double *reward = (double *)(h->out + h->out_off[0]);
+    uint8_t *trunc = h->out + h->out_off[3], *bad = h->out + h->out_off[4];
+    int32_t *step = (int32_t *)(h->out + h->out_off[2]);
+    // Zero-copy form (both buffers pinned, the normal case: KSVecEnv allocates them so): the kernel
+    // reads the actions straight from host memory and its epilogue mirrors every output into the host
+    // block -- the same mirrored, shared-memory-staged stores the multi-GPU exchange uses, with the
+    // host block as the only "peer" -- so the step is ONE launch and a synchronise, no copy calls.
+    static const bool allow_zero_copy = []() { const char *m = getenv("KS_HOST_IO"); return !(m && strcmp(m, "copy") == 0); }();
+    if (allow_zero_copy && device_addressable_host(actions_host) && device_addressable_host(out_host)) {
+        const long long delta = (long long)((uint8_t *)out_host - h->out);
+        int rc = launch_period(h, 1, actions_host, nullptr, obs, reward, trunc, step, bad, 0, nullptr, stream, 1, &delta);
+        if (rc != KS_OK) return rc;
+        KS_CUDA(h, cudaStreamSynchronize(stream));
+        return KS_OK;
+    }
     KS_CUDA(h, cudaMemcpyAsync(h->actions, actions_host, B * h->cfg.J * sizeof(float), cudaMemcpyHostToDevice, stream));
-    int rc = launch_period(h, 1, h->actions, nullptr, (float *)(h->out + h->out_off[1]), (double *)(h->out + h->out_off[0]),
-                           h->out + h->out_off[3], (int32_t *)(h->out + h->out_off[2]), h->out + h->out_off[4], 0, nullptr, stream);
+    int rc = launch_period(h, 1, h->actions, nullptr, obs, reward, trunc, step, bad, 0, nullptr, stream);
     if (rc != KS_OK) return rc;
     KS_CUDA(h, cudaMemcpyAsync(out_host, h->out, h->out_total, cudaMemcpyDeviceToHost, stream));
     KS_CUDA(h, cudaStreamSynchronize(stream));
