@@ -334,14 +334,22 @@ def run_gpu_arm(args):
     acts_host = rng.uniform(-1, 1, (W + K, B, 1, J)).astype(np.float32)
     env.set_state(None, 0)
     for k in range(W):
-        env.step(acts_host[k])
+        obs, rew, term, trunc, info = env.step(acts_host[k])
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize(dev)
+    step_s = []
     t0 = time.perf_counter()
     for k in range(K):
+        t1 = time.perf_counter()
         obs, rew, term, trunc, info = env.step(acts_host[W + k])
+        step_s.append(time.perf_counter() - t1)
     e2e_s = time.perf_counter() - t0
+    if os.environ.get("KS_BENCH_DEBUG"):
+        ss = sorted(step_s)
+        print(f"e2e steps: median {1e3 * ss[len(ss) // 2]:.4f} ms, min {1e3 * ss[0]:.4f}, max {1e3 * ss[-1]:.4f}, "
+              f"5 slowest {[round(1e3 * x, 3) for x in ss[-5:]]}, first 5 {[round(1e3 * x, 3) for x in step_s[:5]]}",
+              file=sys.stderr)
     if world > 1:
         t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

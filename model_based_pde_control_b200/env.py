@@ -159,7 +159,9 @@ class KSVecEnv(VectorEnvBase):
         B, N = num_envs, self.N
         self._out_offsets = [int(x) for x in offs]
         self._out_total = int(total.value)
-        self._blocks = [self._new_block()]          # pinned result blocks (see _free_block)
+        # pinned result blocks (see _free_block); three up front, because a loop that keeps the last
+        # result alive needs two and allocating pinned memory later costs milliseconds
+        self._blocks = [self._new_block() for _ in range(3 if copy else 1)]
         self._out_pinned = self._blocks[0]["pinned"]
         self._act_pinned = torch.empty((B, self.J), dtype=torch.float32, pin_memory=True)
         self._h_act = self._act_pinned.numpy()

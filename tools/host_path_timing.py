@@ -57,6 +57,21 @@ def main():
 
     timeit("ks_step_host_ms", host_call)
     timeit("KSVecEnv_step_ms", lambda: env.step(a_host))
+    keep = {}
+
+    def step_keep():                      # like a training loop: the previous results stay referenced
+        keep["r"] = env.step(a_host)
+
+    timeit("KSVecEnv_step_results_kept_ms", step_keep)
+    many = rng.uniform(-1, 1, (64, B, 1, env.J)).astype(np.float32)
+    it = [0]
+
+    def step_fresh_actions():
+        it[0] += 1
+        keep["r"] = env.step(many[it[0] % 64])
+
+    timeit("KSVecEnv_step_fresh_actions_ms", step_fresh_actions)
+    keep.clear()
     env.copy = False
     timeit("KSVecEnv_step_nocopy_ms", lambda: env.step(a_host))
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
