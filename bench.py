@@ -288,14 +288,13 @@ def run_gpu_arm(args):
             out = gather_packed(out["packed"], fields, B)
         return out
 
-    for k in range(W):
-        one_step(k)
-    torch.cuda.synchronize(dev)
-
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-        time.sleep(0.3)
+        time.sleep(0.3)            # before the warm-up, so that the GPU does not idle between warm-up and timing
+    for k in range(W):
+        one_step(k)
+    torch.cuda.synchronize(dev)
     starts = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
     stops = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
     launches0 = env.launch_count
@@ -321,6 +320,10 @@ def run_gpu_arm(args):
     launches = env.launch_count - launches0
     step_ms = [s.elapsed_time(e) for s, e in zip(starts, stops)]
     total_ms = sum(step_ms)
+    if os.environ.get("KS_BENCH_DEBUG"):
+        ss = sorted(step_ms)
+        print(f"rank {rank} timed steps: median {ss[len(ss) // 2]:.4f} ms, min {ss[0]:.4f}, max {ss[-1]:.4f}, "
+              f"first 3 {[round(x, 4) for x in step_ms[:3]]}", file=sys.stderr)
     if world > 1:
         t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
