@@ -292,6 +292,8 @@ def run_gpu_arm(args):
     if rank == 0:
         sampler.start()
         time.sleep(0.3)            # before the warm-up, so that the GPU does not idle between warm-up and timing
+    if world > 1:
+        dist.barrier()             # nobody enters the first exchange while rank 0 is still sleeping
     for k in range(W):
         one_step(k)
     torch.cuda.synchronize(dev)
