@@ -164,6 +164,41 @@ int ks_gather_connect(ks_handle *h, const void *all_handles);
 int ks_step_gather(ks_handle *h, const float *actions, void **gathered, void *stream);
 int ks_gather_status(ks_handle *h, int32_t *timed_out, void *stream);
 
+/* One step of the reference's data-collection plumbing, fused (two small kernels), for stores of
+ * length 1 as the MBRL loop uses them (mbrl.py:257-275): what StoreNObsVecWrapper.step_wait
+ * (vec_wrappers.py:21-37), StoreNActionsVecWrapper.step_async (:65-72), TransformObsWrapper.step_wait with
+ * a running-min/max ScaleTransform and a SensorTransform (:152-171; transforms.py:141-247) and the
+ * bookkeeping of Worker.rollout (worker.py:68-88) do per env step, after ks_step has written its outputs:
+ *   vminmax    <- min / max over everything seen so far (unless frozen)
+ *   rec_obs    <- obs_store (the stored observation before the step);  rec_nxtobs, obs_store <- obs
+ *   agent_obs  <- ((obs - vmin) / (vmax - vmin)) * scale_width + lower, sampled at [stride/2::stride]
+ *   rec_actions, act_store <- actions;  rec_reward / rec_truncated / rec_step <- reward / truncated / step
+ * All pointers are device memory; float32 arithmetic in exactly this order (no contraction), so the
+ * result equals the element-wise torch / NumPy evaluation bit for bit.  Episode-end steps (final
+ * observation, auto-reset) are handled by the caller. */
+typedef struct ks_collect_args {
+    const float *actions;     /* [B,J]   env-scale actions of this step */
+    const float *obs;         /* [B,No]  ks_step's observation output */
+    const double *reward;     /* [B] */
+    const uint8_t *truncated; /* [B] */
+    const int32_t *step;      /* [B] */
+    float *obs_store;         /* [B,No]  in / out */
+    float *act_store;         /* [B,J]   out */
+    float *vminmax;           /* [2]     running min, max: in / out */
+    float *agent_obs;         /* [B,No'] out, No' = len(range(stride/2, No, stride)) */
+    float *rec_obs, *rec_actions, *rec_nxtobs; /* slot of the transition buffers: [B,No], [B,J], [B,No] */
+    double *rec_reward;       /* [B] */
+    uint8_t *rec_truncated;   /* [B] (bool) */
+    int64_t *rec_step;        /* [B] */
+    float lower, scale_width; /* target range: lower bound and (upper - lower) */
+    int32_t frozen;           /* != 0: vminmax is not updated */
+    int32_t agent_stride;     /* SensorTransform stride on the agent's observation (1 = all) */
+    int64_t *slot_index;      /* NULL: rec_* point at the slot itself.  Else a device counter t: rec_* are
+                                 the bases of [T,B,...] buffers, slot t is written and t incremented by a
+                                 third one-thread kernel -- this form can be captured in a CUDA graph */
+} ks_collect_args;
+int ks_collect(ks_handle *h, const ks_collect_args *args, void *stream);
+
 /* Mirrors np.seterr(over="raise") (kuramoto.py:12): flags[b] != 0 once env b's state went
  * non-finite (sticky until ks_reset / ks_set_state).  Synchronises `stream`.  *any (nullable)
  * receives the OR of all flags; nonfinite_host (nullable) the [B] flags. */

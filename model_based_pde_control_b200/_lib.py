@@ -50,6 +50,16 @@ class KsConfig(ctypes.Structure):
     ]
 
 
+class KsCollectArgs(ctypes.Structure):
+    """``struct ks_collect_args`` (include/ks_b200.h)."""
+
+    _fields_ = [(n, ctypes.c_void_p) for n in (
+        "actions", "obs", "reward", "truncated", "step", "obs_store", "act_store", "vminmax", "agent_obs",
+        "rec_obs", "rec_actions", "rec_nxtobs", "rec_reward", "rec_truncated", "rec_step")] + [
+        ("lower", ctypes.c_float), ("scale_width", ctypes.c_float), ("frozen", ctypes.c_int32),
+        ("agent_stride", ctypes.c_int32), ("slot_index", ctypes.c_void_p)]
+
+
 # every symbol include/ks_b200.h declares: name -> (restype, argtypes)
 _vp, _i32, _u64 = ctypes.c_void_p, ctypes.c_int32, ctypes.c_uint64
 _SIZE5 = ctypes.c_size_t * 5
@@ -74,6 +84,7 @@ EXPORTS = {
     "ks_gather_connect": (ctypes.c_int, [_vp, _vp]),
     "ks_step_gather": (ctypes.c_int, [_vp, _vp, ctypes.POINTER(_vp), _vp]),
     "ks_gather_status": (ctypes.c_int, [_vp, ctypes.POINTER(_i32), _vp]),
+    "ks_collect": (ctypes.c_int, [_vp, ctypes.POINTER(KsCollectArgs), _vp]),
     "ks_bench_fp64_peak": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                           ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]),
 }

@@ -66,6 +66,8 @@ struct ks_handle {
     uint32_t g_epoch = 0;
     int32_t *g_timeout = nullptr;   // device flag set by the wait kernel when a peer never signalled
     size_t g_slot = 0, g_flags_off = 0, g_total = 0;
+    int32_t *collect_keys = nullptr;   // [2 parities][2]: ordered-int min / max keys of ks_collect
+    uint32_t collect_calls = 0;
     size_t out_off[5] = {0, 0, 0, 0, 0}, out_total = 0;
     uint64_t launches = 0;
     char err[256] = "";
@@ -317,6 +319,84 @@ __global__ void gather_signal_wait(uint32_t *const *peer_flags, volatile uint32_
     __threadfence_system();
 }
 
+// ---- ks_collect: fused wrapper plumbing --------------------------------------------------------------
+__device__ __forceinline__ int float_key(float f)       // monotonic float -> int map (for atomicMin / Max)
+{
+    const int i = __float_as_int(f);
+    return i >= 0 ? i : i ^ 0x7fffffff;
+}
+__device__ __forceinline__ float key_float(int k) { return __int_as_float(k >= 0 ? k : k ^ 0x7fffffff); }
+
+__global__ void collect_minmax(const float *__restrict__ obs, size_t n, int32_t *__restrict__ keys)
+{
+    float lo = INFINITY, hi = -INFINITY;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const float v = obs[i];
+        lo = fminf(lo, v);
+        hi = fmaxf(hi, v);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+        hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicMin(&keys[0], float_key(lo));
+        atomicMax(&keys[1], float_key(hi));
+    }
+}
+
+__global__ void collect_apply(const ks_collect_args a, int B, int No, int J, const int32_t *__restrict__ keys,
+                              int32_t *__restrict__ next_keys)
+{
+    float vmin = a.vminmax[0], vmax = a.vminmax[1];
+    if (!a.frozen) {
+        vmin = fminf(vmin, key_float(keys[0]));
+        vmax = fmaxf(vmax, key_float(keys[1]));
+    }
+    const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
+    if (gid == 0) {
+        // every thread merges the same two pairs, so whether it read the old or the merged running
+        // bounds does not matter; the other parity's keys are re-armed for the next call
+        a.vminmax[0] = vmin;
+        a.vminmax[1] = vmax;
+        next_keys[0] = 0x7fffffff;
+        next_keys[1] = (int32_t)0x80000000;
+    }
+    const float width = __fsub_rn(vmax, vmin);
+    const int first = a.agent_stride / 2;
+    const int Na = (No - first + a.agent_stride - 1) / a.agent_stride;
+    const size_t n = (size_t)B * No;
+    const size_t t = a.slot_index ? (size_t)*a.slot_index : 0;      // incremented by collect_advance afterwards
+    float *rec_obs = a.rec_obs + t * n, *rec_nxtobs = a.rec_nxtobs + t * n, *rec_actions = a.rec_actions + t * (size_t)B * J;
+    double *rec_reward = a.rec_reward + t * B;
+    uint8_t *rec_truncated = a.rec_truncated + t * B;
+    int64_t *rec_step = a.rec_step + t * B;
+    for (size_t i = gid; i < n; i += stride) {
+        const float x = a.obs[i];
+        rec_obs[i] = a.obs_store[i];
+        rec_nxtobs[i] = x;
+        a.obs_store[i] = x;
+        const int b = (int)(i / No), c = (int)(i % No) - first;
+        if (c >= 0 && c % a.agent_stride == 0) {
+            const float s = __fadd_rn(__fmul_rn(__fdiv_rn(__fsub_rn(x, vmin), width), a.scale_width), a.lower);
+            a.agent_obs[(size_t)b * Na + c / a.agent_stride] = s;
+        }
+    }
+    for (size_t i = gid; i < (size_t)B * J; i += stride) {
+        const float v = a.actions[i];
+        rec_actions[i] = v;
+        a.act_store[i] = v;
+    }
+    for (size_t i = gid; i < (size_t)B; i += stride) {
+        rec_reward[i] = a.reward[i];
+        rec_truncated[i] = a.truncated[i] != 0 ? 1 : 0;
+        rec_step[i] = (int64_t)a.step[i];
+    }
+}
+
+__global__ void collect_advance(int64_t *slot_index) { *slot_index += 1; }
+
 int launch_period(ks_handle *h, int K, const float *actions, const float *phi, float *obs, double *reward,
                   uint8_t *truncated, int32_t *step, uint8_t *nonfinite_out, int reset_timestep, const uint8_t *mask,
                   cudaStream_t stream, int n_remote = 0, const long long *remote_delta = nullptr)
@@ -473,6 +553,11 @@ int ks_create(const ks_config *cfg, ks_handle **out)
         KS_TRY(cudaMalloc(&h->out, h->out_total));
         KS_TRY(cudaMalloc(&h->scratch64, B * N * sizeof(double)));
         KS_TRY(cudaMalloc(&h->mask, B));
+        KS_TRY(cudaMalloc(&h->collect_keys, 4 * sizeof(int32_t)));
+        {
+            const int32_t init[4] = {0x7fffffff, (int32_t)0x80000000, 0x7fffffff, (int32_t)0x80000000};
+            KS_TRY(cudaMemcpy(h->collect_keys, init, sizeof(init), cudaMemcpyHostToDevice));
+        }
         KS_TRY(cudaMemset(h->u, 0, B * N * esz));
         KS_TRY(cudaMemset(h->timestep, 0, B * sizeof(int32_t)));
         KS_TRY(cudaMemset(h->nonfinite, 0, B));
@@ -512,6 +597,7 @@ int ks_destroy(ks_handle *h)
         cudaFree(h->out);
         cudaFree(h->scratch64);
         cudaFree(h->mask);
+        cudaFree(h->collect_keys);
         cudaFree(h->etd_tables);
         if (h->g_connected)
             for (int r = 0; r < h->g_world; ++r)
@@ -830,6 +916,39 @@ int ks_gather_status(ks_handle *h, int32_t *timed_out, void *stream_)
     DeviceGuard guard(h->cfg.device);
     KS_CUDA(h, cudaMemcpyAsync(timed_out, h->g_timeout, sizeof(int32_t), cudaMemcpyDeviceToHost, (cudaStream_t)stream_));
     KS_CUDA(h, cudaStreamSynchronize((cudaStream_t)stream_));
+    return KS_OK;
+}
+
+int ks_collect(ks_handle *h, const ks_collect_args *a, void *stream_)
+{
+    if (!h || !a) return h ? fail(h, KS_ERR_ARG, "ks_collect: NULL argument") : KS_ERR_ARG;
+    if (!a->actions || !a->obs || !a->reward || !a->truncated || !a->step || !a->obs_store || !a->act_store || !a->vminmax ||
+        !a->agent_obs || !a->rec_obs || !a->rec_actions || !a->rec_nxtobs || !a->rec_reward || !a->rec_truncated || !a->rec_step)
+        return fail(h, KS_ERR_ARG, "ks_collect: NULL buffer");
+    if (a->agent_stride < 1 || a->agent_stride > h->obs_len) return fail(h, KS_ERR_ARG, "ks_collect: bad agent_stride");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    DeviceGuard guard(h->cfg.device);
+    const int B = h->cfg.num_envs, No = h->obs_len, J = h->cfg.J;
+    const size_t n = (size_t)B * No;
+    // The min / max keys of one call are re-armed by the NEXT call's apply kernel (parity slots).  A
+    // call captured in a CUDA graph replays with the parity it was captured with; its keys then simply
+    // keep accumulating, which is the running minimum / maximum the caller merges them into anyway.
+    int32_t *keys = h->collect_keys + 2 * (h->collect_calls & 1u), *next = h->collect_keys + 2 * ((h->collect_calls + 1) & 1u);
+    h->collect_calls += 1;
+    const unsigned blocks = (unsigned)((n + 1023) / 1024 < 592 ? (n + 1023) / 1024 : 592);
+    if (!a->frozen) {
+        collect_minmax<<<blocks, 256, 0, stream>>>(a->obs, n, keys);
+        KS_CUDA(h, cudaGetLastError());
+        h->launches += 1;
+    }
+    collect_apply<<<blocks, 256, 0, stream>>>(*a, B, No, J, keys, next);
+    KS_CUDA(h, cudaGetLastError());
+    h->launches += 1;
+    if (a->slot_index) {
+        collect_advance<<<1, 1, 0, stream>>>(a->slot_index);
+        KS_CUDA(h, cudaGetLastError());
+        h->launches += 1;
+    }
     return KS_OK;
 }
 

@@ -35,6 +35,7 @@ class ScaleTransformDevice:
         self.vmin = None if bounds[0] is None else torch.as_tensor(bounds[0], dtype=torch.float32).amin()
         self.vmax = None if bounds[1] is None else torch.as_tensor(bounds[1], dtype=torch.float32).amax()
         self.frozen = frozen
+        self.minmax = None
 
     def _on(self, device):
         """Keep the running bounds on the data's device (a per-call ``.to`` of a CPU scalar is a
@@ -52,7 +53,8 @@ class ScaleTransformDevice:
         lo, hi = lo.to(torch.float32), hi.to(torch.float32)
         # in place once the bounds exist: a captured CUDA graph keeps pointing at these tensors
         if self.vmin is None:
-            self.vmin, self.vmax = lo.clone(), hi.clone()
+            self.minmax = torch.stack([lo, hi])            # one 2-element tensor: ks_collect updates it in place
+            self.vmin, self.vmax = self.minmax[0], self.minmax[1]
         else:
             torch.minimum(lo, self.vmin, out=self.vmin)
             torch.maximum(hi, self.vmax, out=self.vmax)
@@ -95,12 +97,15 @@ class DeviceEnvPipeline:
                        reset_device(seed=...), get_state_device()`` (``KSVecEnv``)
     ``num_steps``      history length of the obs / action stores (1 in the reference's MBRL loop)
     ``obs_scale``      target range of the running min/max observation scaling
+    ``fused``          let ``rollout`` use ``ks_collect`` (two CUDA kernels per step for the whole store /
+                       scaling / record bookkeeping) when the env provides it; results are bitwise
+                       those of the tensor-op path
     ``action_bounds``  ``(low, high)`` of the env's action space; agent actions in ``[-1,1]`` are mapped
                        onto it (identity for the KS env), frozen like the reference's ``ascaling``
     """
 
     def __init__(self, env, num_steps: int = 1, obs_scale=(-1.0, 1.0), frozen_obs_scaling: bool = False,
-                 action_bounds=(-1.0, 1.0), agent_sensor_stride: int = 1):
+                 action_bounds=(-1.0, 1.0), agent_sensor_stride: int = 1, fused: bool = True):
         self.env = env
         self.B = env.num_envs
         self.num_steps = num_steps
@@ -109,6 +114,7 @@ class DeviceEnvPipeline:
         self.agent_sensor = SensorTransformDevice(agent_sensor_stride)
         self.obs_store = self.finals = self.act_store = None
         self._obs_row = self._act_row = None
+        self.fused = fused                 # use the env library's ks_collect kernels where possible
         self._rollout_buf = {}
         self._graphs = {}
         self._episode_step = None          # host-side step counter (all envs synchronous)
@@ -240,9 +246,31 @@ class DeviceEnvPipeline:
                 steps=torch.empty(lead, dtype=torch.int64, device=dev))
             if reuse_buffers:
                 self._rollout_buf = {key: buf}
+        # ks_collect (two small CUDA kernels of the env library) does the per-step bookkeeping when the
+        # env offers it, the stores have length 1 and the step does not end the episode; everything
+        # else goes through step() and tensor copies.  Both paths keep the same in-place state.
+        fused = (self.fused and hasattr(self.env, "collect_step") and S == 1 and last_obs.is_cuda
+                 and self.oscaling.minmax is not None and self.act_store.is_contiguous() and self.obs_store.is_contiguous())
+        agent_buf = torch.empty_like(last_obs) if fused else None
+        stale = False                                # last_stored out of date (fused steps do not maintain it)
         for t in range(num_steps):
             with torch.no_grad():
                 actions = select_action(last_obs)
+            if fused and self._episode_step + 1 < self.env.max_episode_steps:
+                a = self.ascaling.inverse(actions.to(torch.float32).reshape(self.B, 1, self.env.J)).contiguous()
+                out = self.env.step_device(a.reshape(self.B, self.env.J))
+                self.env.collect_step(actions=a, out=out, obs_store=self.obs_store, act_store=self.act_store,
+                                      vminmax=self.oscaling.minmax, agent_obs=agent_buf,
+                                      rec=(buf.obs[t], buf.actions[t], buf.nxtobs[t], buf.rewards[t], buf.truncated[t],
+                                           buf.steps[t]),
+                                      lower=self.oscaling.lower, upper=self.oscaling.upper, frozen=self.oscaling.frozen,
+                                      agent_stride=self.agent_sensor.stride)
+                self._act_row[0] = self._obs_row[0] = True
+                self._episode_step += 1
+                last_obs, stale = agent_buf, True
+                continue
+            if stale:
+                last_stored, stale = self._valid(self.obs_store, self._obs_row), False
             last_obs, rewards, terminated, truncated, infos = self.step(actions)
             buf.obs[t].copy_(last_stored)
             last_stored = self._valid(self.obs_store, self._obs_row)
@@ -254,6 +282,8 @@ class DeviceEnvPipeline:
             buf.rewards[t].copy_(rewards)
             buf.truncated[t].copy_(truncated)
             buf.steps[t].copy_(infos["step"])
+        if fused:
+            last_obs = last_obs.clone()              # agent_buf is reused by the next fused step
         return buf, last_obs
 
     # -- CUDA-graph rollout ----------------------------------------------------------------------
@@ -309,6 +339,22 @@ class DeviceEnvPipeline:
             obs_in.copy_(new_obs)
             t_idx.add_(1)
 
+        use_collect = (self.fused and hasattr(self.env, "collect_step") and self.oscaling.minmax is not None
+                       and self.act_store.is_contiguous() and self.obs_store.is_contiguous())
+
+        def fused_step():                            # the regular step with ks_collect: ~22 kernels, no tensor-op bookkeeping
+            with torch.no_grad():
+                actions = select_action(obs_in)
+            a = self.ascaling.inverse(actions.to(torch.float32).reshape(self.B, 1, self.env.J)).contiguous()
+            out = self.env.step_device(a.reshape(self.B, self.env.J))
+            self.env.collect_step(actions=a, out=out, obs_store=self.obs_store, act_store=self.act_store,
+                                  vminmax=self.oscaling.minmax, agent_obs=obs_in,
+                                  rec=(buf.obs, buf.actions, buf.nxtobs, buf.rewards, buf.truncated, buf.steps),
+                                  lower=self.oscaling.lower, upper=self.oscaling.upper,
+                                  frozen=self.oscaling.frozen, agent_stride=self.agent_sensor.stride, slot_index=t_idx)
+            self._episode_step += 1
+
+        regular_step = fused_step if use_collect else one_step
         for _ in range(num_steps):
             if self._episode_step + 1 >= self.env.max_episode_steps:
                 one_step()                           # episode end: eager (auto-reset inside step())
@@ -320,13 +366,13 @@ class DeviceEnvPipeline:
                 side = torch.cuda.Stream(device=dev)
                 side.wait_stream(torch.cuda.current_stream(dev))
                 with torch.cuda.stream(side):
-                    one_step()
+                    regular_step()
                 torch.cuda.current_stream(dev).wait_stream(side)
                 if self._episode_step + 1 < self.env.max_episode_steps:
                     graph = torch.cuda.CUDAGraph()
                     host_count = self._episode_step
                     with torch.cuda.graph(graph):
-                        one_step()
+                        regular_step()
                     self._episode_step = host_count      # undo the capture's host-side bookkeeping
                     g["graph"] = graph
                 continue

@@ -469,6 +469,26 @@ class KSVecEnv(VectorEnvBase):
                                               self._stream()))
         return out
 
+    # ------------------------------------------------------------------ fused wrapper plumbing
+    def collect_step(self, *, actions, out, obs_store, act_store, vminmax, agent_obs, rec, lower: float,
+                     upper: float, frozen: bool, agent_stride: int, slot_index=None) -> None:
+        """``ks_collect``: the per-step bookkeeping of the reference's wrapper stack + ``Worker.rollout``
+        (stores of length 1) in two small kernels instead of ~20 tensor ops.  ``out`` = the dict
+        ``step_device`` returned, ``rec`` = ``(obs, actions, nxtobs, reward, truncated, step)`` slot views
+        of the transition buffers -- or, with ``slot_index`` (a CUDA int64 counter), the whole ``[T,B,...]``
+        buffers, of which slot ``t`` is written and ``t`` incremented on the device (graph-capturable);
+        everything contiguous CUDA tensors."""
+        r_obs, r_act, r_nxt, r_rew, r_trunc, r_step = rec
+        a = _lib.KsCollectArgs(
+            actions=actions.data_ptr(), obs=out["obs"].data_ptr(), reward=out["reward"].data_ptr(),
+            truncated=out["truncated"].data_ptr(), step=out["step"].data_ptr(), obs_store=obs_store.data_ptr(),
+            act_store=act_store.data_ptr(), vminmax=vminmax.data_ptr(), agent_obs=agent_obs.data_ptr(),
+            rec_obs=r_obs.data_ptr(), rec_actions=r_act.data_ptr(), rec_nxtobs=r_nxt.data_ptr(),
+            rec_reward=r_rew.data_ptr(), rec_truncated=r_trunc.data_ptr(), rec_step=r_step.data_ptr(),
+            lower=float(lower), scale_width=float(upper - lower), frozen=int(bool(frozen)), agent_stride=int(agent_stride),
+            slot_index=None if slot_index is None else slot_index.data_ptr())
+        _lib.check(self._h, self._lib.ks_collect(self._h, ctypes.byref(a), self._stream()))
+
     # ------------------------------------------------------------------ fused all-gather (multi-GPU)
     def gather_init(self, world: int, rank: int) -> bytes:
         """Allocate this rank's gather buffer (``ks_gather_init``); returns the 64-byte CUDA-IPC

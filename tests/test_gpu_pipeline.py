@@ -130,3 +130,44 @@ def test_cuda_graph_rollout_equals_eager_rollout():
     for a, b in zip(*res):
         assert a.shape == b.shape and torch.equal(a, b)
     assert res[1][5].sum() == 2 * B                           # two episode ends inside the 23 steps
+
+
+@pytest.mark.parametrize("agent_stride,env_stride", [(1, 1), (4, 1), (1, 2)])
+def test_fused_collect_kernels_equal_tensor_op_path(agent_stride, env_stride):
+    """rollout(fused=True) -- ks_collect: running min/max, scaling, stores and the transition record
+    in two CUDA kernels per step -- against the tensor-op path that is pinned to the reference's
+    wrappers (tests/test_device_pipeline.py): bitwise, across episode boundaries."""
+    import torch
+    from model_based_pde_control_b200 import DeviceEnvPipeline, KSVecEnv
+
+    B, T = 48, 27
+    cfg = dict(cfg_steps=10, Tmax=0.1)                        # 10-step episodes
+    torch.manual_seed(1)
+    No = 64 // env_stride
+    Na = len(range(agent_stride // 2, No, agent_stride))
+    W = torch.randn(Na, 4, device="cuda") * 0.5
+
+    def policy(o):
+        return torch.tanh(o.reshape(o.shape[0], -1) @ W).reshape(-1, 1, 4)
+
+    res = []
+    for fused in (False, True):
+        env = KSVecEnv(B, cfg, ic="device", burnin_periods=2, sensor_stride=env_stride)
+        pipe = DeviceEnvPipeline(env, agent_sensor_stride=agent_stride, fused=fused)
+        last = pipe.reset(seed=4)
+        orig, counter = env.reset_device, [0]
+
+        def seeded(seed=None, **kw):
+            counter[0] += 1
+            return orig(seed=2000 + counter[0] if seed is None else seed, **kw)
+
+        env.reset_device = seeded
+        launches = env.launch_count
+        batch, last = pipe.rollout(policy, T, last_obs=last)
+        res.append([t.clone() for t in batch] + [last.clone(), pipe.oscaling.vmin.clone(), pipe.oscaling.vmax.clone(),
+                                                 pipe.obs_store.clone(), pipe.act_store.clone()])
+        per_step = (env.launch_count - launches) / T
+        env.close()
+    for a, b in zip(*res):
+        assert a.shape == b.shape and torch.equal(a, b)
+    assert per_step > 2.5          # fused run: period kernel + 2 collect kernels on most steps

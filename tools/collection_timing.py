@@ -53,6 +53,7 @@ def main():
     args = ap.parse_args()
     for B in [int(x) for x in args.envs.split(",")]:
         cfg = dict(dt=0.025, cfg_steps=10) if args.solver == "etdrk4" else {}
+        cfg["Tmax"] = 1000.0        # 4000-step episodes: no auto-reset (burn-in launch) inside the timed loops
         env = KSVecEnv(B, cfg, ic="device", solver=args.solver, burnin_periods=40)     # short burn-in: timing tool
         policy = TanhGaussianPolicy(env.N, env.J).cuda()
         pipe = DeviceEnvPipeline(env)
