@@ -773,7 +773,8 @@ int ks_step_host(ks_handle *h, const float *actions_host, void *out_host, void *
     // block -- the same mirrored, shared-memory-staged stores the multi-GPU exchange uses, with the
     // host block as the only "peer" -- so the step is ONE launch and a synchronise, no copy calls.
     static const bool allow_zero_copy = []() { const char *m = getenv("KS_HOST_IO"); return !(m && strcmp(m, "copy") == 0); }();
-    if (allow_zero_copy && device_addressable_host(actions_host) && device_addressable_host(out_host)) {
+    // (sensor-strided observations are written element by element: those go through the copy form)
+    if (allow_zero_copy && h->cfg.obs_stride <= 1 && device_addressable_host(actions_host) && device_addressable_host(out_host)) {
         const long long delta = (long long)((uint8_t *)out_host - h->out);
         int rc = launch_period(h, 1, actions_host, nullptr, obs, reward, trunc, step, bad, 0, nullptr, stream, 1, &delta);
         if (rc != KS_OK) return rc;
