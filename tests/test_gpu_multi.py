@@ -29,7 +29,7 @@ dev = torch.device("cuda", local)
 dist.init_process_group("nccl", device_id=dev)
 solver = os.environ.get("KS_SOLVER", "fd_rk4")
 cfg = dict(dt=0.025, cfg_steps=10) if solver == "etdrk4" else dict(cfg_steps=25)
-B_total, K = 1024, 12
+B_total, K = 1020, 12      # 510 envs per rank at world 2: the last thread block has an early-exit warp
 lo, hi = shard_range(B_total, rank, world)
 rng = np.random.default_rng(0)
 u0 = rng.uniform(-1, 1, (B_total, 64))
