@@ -27,8 +27,8 @@
 //     core (whose transpose then runs inside the 8 lanes that share pl mod R) the R lanes that differ
 //     in pl mod R are combined by one / two radix-2 butterfly stages with warp shuffles (twiddles
 //     W_8R^(m1 s) before, a -i rotation between the stages); the spectral layout becomes lane
-//     (m1', k2 = pl / R), register s  <->  k = 64 bitrev(m1') + 8 s + k2, which only the host-side
-//     table permutation needs to know.
+//     (m1', k2 = pl / R), register s  <->  k = 64 bitrev(m1') + 8 s + k2, which only the
+//     table permutation at kernel start needs to know.
 //   * HBM is touched at control-period boundaries only (state in, state / observation / reward out).
 #pragma once
 
