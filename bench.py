@@ -277,8 +277,23 @@ def run_gpu_arm(args):
 
     fields = env.packed_fields()
     fused = world > 1 and args.gather == "fused"
+    gather_note = None
     if fused:
-        connect_fused_gather(env)     # CUDA-IPC handles exchanged once; afterwards no collective call per period
+        # CUDA-IPC handles exchanged once; afterwards no collective call per period.  If peer mapping is
+        # not possible on this box (ranks in different IPC namespaces, no P2P), every rank switches to
+        # the NCCL all-gather together and the JSON line says so -- the exchange is never skipped.
+        try:
+            connect_fused_gather(env)
+            ok = 1
+        except Exception as exc:          # noqa: BLE001 - reported below, on every rank
+            ok, gather_note = 0, f"{type(exc).__name__}: {exc}"
+        flag = torch.tensor([ok], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 0:
+            fused = False
+            args.gather = "nccl"
+            gather_note = "fused exchange unavailable (" + (gather_note or "a peer could not map the buffers") + "); NCCL all-gather used"
+            print(gather_note, file=sys.stderr)
 
     def one_step(k):
         if fused:
@@ -413,6 +428,7 @@ def run_gpu_arm(args):
                 if fused else ("one NCCL all-gather of the packed obs/reward/step/truncated/flags block per period, timed"
                                if args.gather == "nccl" else "NONE (diagnostic run: every rank keeps its shard to itself)")),
             "layout": env.launch_info(),
+            **({"collective_note": gather_note} if gather_note else {}),
         },
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": env.h2d_bytes_per_step,
                 "d2h_bytes_per_step": env.d2h_bytes_per_step, "ms_per_step": 1e3 * e2e_s / K,
