@@ -283,16 +283,11 @@ def run_gpu_arm(args):
         # not possible on this box (ranks in different IPC namespaces, no P2P), every rank switches to
         # the NCCL all-gather together and the JSON line says so -- the exchange is never skipped.
         try:
-            connect_fused_gather(env)
-            ok = 1
-        except Exception as exc:          # noqa: BLE001 - reported below, on every rank
-            ok, gather_note = 0, f"{type(exc).__name__}: {exc}"
-        flag = torch.tensor([ok], device=dev)
-        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-        if int(flag.item()) == 0:
+            connect_fused_gather(env)         # raises on every rank if any rank fails
+        except Exception as exc:              # noqa: BLE001 - reported in the JSON line
             fused = False
             args.gather = "nccl"
-            gather_note = "fused exchange unavailable (" + (gather_note or "a peer could not map the buffers") + "); NCCL all-gather used"
+            gather_note = f"fused exchange unavailable ({type(exc).__name__}: {exc}); NCCL all-gather used"
             print(gather_note, file=sys.stderr)
 
     def one_step(k):

@@ -77,15 +77,32 @@ def gather_packed(packed_local: torch.Tensor, fields: dict, local_envs: int, gro
 def connect_fused_gather(env, group=None) -> None:
     """Set up the fused all-gather of ``env`` (a local ``KSVecEnv`` shard) across ``group``: every
     rank allocates its gather buffer, the 64-byte CUDA-IPC handles travel through one host-side
-    ``all_gather_object``, every rank maps its peers' buffers.  Equal shards only (checked)."""
+    ``all_gather_object``, every rank maps its peers' buffers.  Equal shards only (checked).
+    A failure on any rank (no peer access, different IPC namespaces, ...) raises on EVERY rank, after
+    the ranks have agreed on it -- nobody is left waiting in a collective."""
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
-    handle = env.gather_init(world, rank)
+    err, handle = None, b""
+    try:
+        handle = env.gather_init(world, rank)
+    except Exception as exc:      # noqa: BLE001 - agreed on below
+        err = f"rank {rank}: {type(exc).__name__}: {exc}"
     infos = [None] * world
-    dist.all_gather_object(infos, (env.num_envs, handle), group=group)
-    if len({n for n, _ in infos}) != 1:
-        raise ValueError(f"fused gather needs equal shards, got {[n for n, _ in infos]}")
-    env.gather_connect([h for _, h in infos])
+    dist.all_gather_object(infos, (env.num_envs, handle, err), group=group)
+    errors = [e for _, _, e in infos if e]
+    if errors:
+        raise RuntimeError("fused gather: buffer allocation failed: " + "; ".join(errors))
+    if len({n for n, _, _ in infos}) != 1:
+        raise ValueError(f"fused gather needs equal shards, got {[n for n, _, _ in infos]}")
+    try:
+        env.gather_connect([h for _, h, _ in infos])
+    except Exception as exc:      # noqa: BLE001
+        err = f"rank {rank}: {type(exc).__name__}: {exc}"
+    outcomes = [None] * world
+    dist.all_gather_object(outcomes, err, group=group)
+    errors = [e for e in outcomes if e]
+    if errors:
+        raise RuntimeError("fused gather: peer mapping failed: " + "; ".join(errors))
     dist.barrier(group)      # nobody launches a peer-writing kernel before everyone is mapped
 
 

@@ -148,3 +148,42 @@ def test_fused_gather_setup(world, num_envs):
         assert p.exitcode == 0
     results = dict(q.get(timeout=5) for _ in range(world))
     assert results == {r: True for r in range(world)}
+
+
+class FailingGatherEnv(StubGatherEnv):
+    def __init__(self, n, fail_rank):
+        super().__init__(n)
+        self.fail_rank = fail_rank
+
+    def gather_connect(self, handles):
+        if self.rank == self.fail_rank:
+            raise OSError("no peer access")
+        super().gather_connect(handles)
+
+
+def _failing_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from model_based_pde_control_b200.sharding import connect_fused_gather
+        try:
+            connect_fused_gather(FailingGatherEnv(8, fail_rank=1))
+            q.put((rank, False))
+        except RuntimeError as exc:       # every rank, not only the one that failed
+            q.put((rank, "rank 1" in str(exc) and "no peer access" in str(exc)))
+        dist.barrier()                    # and nobody is stuck in a half-finished collective
+    finally:
+        dist.destroy_process_group()
+
+
+def test_fused_gather_setup_failure_is_raised_on_every_rank():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_failing_worker, args=(r, 3, port, q)) for r in range(3)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert dict(q.get(timeout=5) for _ in range(3)) == {0: True, 1: True, 2: True}
