@@ -162,6 +162,7 @@ class KSVecEnv(VectorEnvBase):
         # pinned result blocks (see _free_block); three up front, because a loop that keeps the last
         # result alive needs two and allocating pinned memory later costs milliseconds
         self._blocks = [self._new_block() for _ in range(3 if copy else 1)]
+        self._spill = None
         self._out_pinned = self._blocks[0]["pinned"]
         self._act_pinned = torch.empty((B, self.J), dtype=torch.float32, pin_memory=True)
         self._h_act = self._act_pinned.numpy()
@@ -399,10 +400,10 @@ class KSVecEnv(VectorEnvBase):
             blk = self._new_block()
             self._blocks.append(blk)
             return blk
-        if "spill" not in self.__dict__:
-            self.spill = self._new_block()
-        self.spill["owned"] = False
-        return self.spill
+        if self._spill is None:
+            self._spill = self._new_block()
+        self._spill["owned"] = False
+        return self._spill
 
     def _observe(self, u: np.ndarray) -> np.ndarray:
         """float32 observation ``(B,1,No)`` of states ``u [B,N]`` (cast + sensor sampling)."""

@@ -96,7 +96,7 @@ def test_result_blocks_are_reused_only_when_no_result_references_them():
     B, No = 6, 8
     offs = [0, 48, 48 + 192, 48 + 192 + 32, 48 + 192 + 32 + 16]
     fake = types.SimpleNamespace(num_envs=B, obs_len=No, _out_offsets=offs, _out_total=offs[4] + 16, copy=True,
-                                 MAX_RESULT_BLOCKS=3, _block_refs=KSVecEnv._block_refs)
+                                 MAX_RESULT_BLOCKS=3, _block_refs=KSVecEnv._block_refs, _spill=None)
     fake._new_block = lambda: KSVecEnv._new_block(fake)
     fake._blocks = [fake._new_block()]
     free = lambda: KSVecEnv._free_block(fake)
