@@ -154,14 +154,15 @@ void etd_tables_host(int N, double L, double h, bool dealias, std::vector<double
 }
 
 // Points per lane P for a grid of N points and a batch of B envs (lanes = N / P must fit one warp).
-// Static cost model fitted to B200 measurements (profiles/README.md sections 4 and 10), cycles per RK4
+// Static cost model fitted to B200 measurements (profiles/README.md sections 10 and 12), cycles per RK4
 // sub-step of the fullest SM sub-partition (SMSP), which is what the launch takes:
 //     T(P) = max( L(P), w * c(P) ),   w = ceil(warps(P) / #SMSP),   warps(P) = ceil(B / (32 / lanes))
-//     c(P) = 196 P + 135   a warp's share of a saturated SMSP (register-file operand bandwidth bound)
-//     L(P) = 184 P + 460   one warp alone: its dependent-issue latency (1198 / 2115 / 3404 cycles
+//     c(P) = 182 P + 130   a warp's share of a saturated SMSP (859 / 1640 / 3048 cycles measured for
+//                          P = 4 / 8 / 16 at 65 536 envs)
+//     L(P) = 169 P + 430   one warp alone: its dependent-issue latency (1105 / 1915 / 3135 cycles
 //                          measured for P = 4 / 8 / 16)
-// Small batches therefore run with few points per lane (10 envs: 0.15 ms per period with P = 4
-// against 0.43 ms with P = 16), large ones with many (less halo overhead per point).  Smallest T
+// Small batches therefore run with few points per lane (10 envs: 0.14 ms per period with P = 4
+// against 0.40 ms with P = 16), large ones with many (less halo overhead per point).  Smallest T
 // wins; a larger P wins ties within 0.5 %.  The choice is deterministic in (N, B, #SM) so that
 // every rank of a sharded run picks the same layout.
 int choose_points_per_lane(int N, long long B, int sm_count)
@@ -176,8 +177,8 @@ int choose_points_per_lane(int N, long long B, int sm_count)
         const long long epw = 32 / lanes;
         const long long warps = (B + epw - 1) / epw;
         const long long per_smsp = (warps + smsp - 1) / smsp;
-        double t = (double)per_smsp * (196.0 * P + 135.0);
-        const double alone = 184.0 * P + 460.0;
+        double t = (double)per_smsp * (182.0 * P + 130.0);
+        const double alone = 169.0 * P + 430.0;
         if (t < alone) t = alone;
         if (best == 0 || t <= best_t * 1.005) { best_t = t < best_t || best == 0 ? t : best_t; best = P; }
     }
