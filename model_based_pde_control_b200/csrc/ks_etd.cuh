@@ -36,6 +36,9 @@
 
 namespace ks {
 
+#ifndef KS_ETD_MIN_BLOCKS
+#define KS_ETD_MIN_BLOCKS 2
+#endif
 constexpr int kEtdN = 64;          // grid points of the base layout; the kernel handles N = 64 R, R = 1, 2, 4
 // Per-wavenumber tables, each [N] in natural FFT order (host-precomputed, ks_api.cu).  The kernel
 // carries the nonlinear terms pre-multiplied by Q (N~ = Q N), which removes Q from the stage
@@ -300,7 +303,7 @@ struct EtdParams {
 // The spectral control-period kernel: K periods x cfg_steps ETDRK4 steps, 8/R envs per warp.
 // ---------------------------------------------------------------------------------------------
 template <typename T, int R, int RMODE>
-__global__ void __launch_bounds__(kBlockThreads) ks_etd_kernel(const EtdParams ep)
+__global__ void __launch_bounds__(kBlockThreads, KS_ETD_MIN_BLOCKS) ks_etd_kernel(const EtdParams ep)
 {
     static_assert(R == 1 || R == 2 || R == 4, "N = 64 R with R = 1, 2, 4");
     const Params &p = ep.p;
