@@ -387,6 +387,10 @@ def run_gpu_arm(args):
     rc = lib.ks_bench_fp64_peak(local_rank, 20000, 5, ctypes.byref(best), ctypes.byref(mean))
     fp64_peak = best.value if rc == 0 and best.value > 0 else FP64_NOMINAL_TFLOPS
     peak_src = "self-measured DFMA micro-kernel (ks_bench_fp64_peak, best of 5)" if rc == 0 else "nominal"
+    bound, kernel_peak, nominal = "fp64", fp64_peak, FP64_NOMINAL_TFLOPS
+    if args.precision == "f32":        # optional fp32 mode: the FP32 FMA pipes bound it (no self-measured figure)
+        bound, kernel_peak, nominal = "fp32", 2 * FP64_NOMINAL_TFLOPS, 2 * FP64_NOMINAL_TFLOPS
+        peak_src = "nominal 148 SM x 128 lanes x 2 x 1.965 GHz"
     peaks = {}
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -432,10 +436,10 @@ def run_gpu_arm(args):
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {
-            "bound": "fp64", "kernel": "ks_period_kernel", "achieved": achieved_tf, "peak": fp64_peak,
-            "unit": "TFLOP/s", "frac": achieved_tf / fp64_peak, "traffic": traffic,
+            "bound": bound, "kernel": "ks_period_kernel", "achieved": achieved_tf, "peak": kernel_peak,
+            "unit": "TFLOP/s", "frac": achieved_tf / kernel_peak, "traffic": traffic,
             "traffic_unit": "bytes per launch (dram read+write, ncu --set full)", "traffic_source": traffic_src,
-            "peak_source": peak_src, "peak_nominal": FP64_NOMINAL_TFLOPS, "frac_of_nominal": achieved_tf / FP64_NOMINAL_TFLOPS,
+            "peak_source": peak_src, "peak_nominal": nominal, "frac_of_nominal": achieved_tf / nominal,
             "flops_per_launch": flops_per_launch, "flops_model": "191*N*cfg_steps per env-period (SURVEY.md 8d)",
             "kernel_ms": kernel_ms,
             "hbm": {"achieved": hbm_achieved, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_achieved / hbm_peak,
