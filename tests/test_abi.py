@@ -40,6 +40,23 @@ def test_config_struct_layout_matches_header():
     assert ctypes.sizeof(_lib.KsConfig) == 14 * 4 + 2 * 8 + 8
 
 
+def test_collect_args_struct_layout_matches_header():
+    """ks_collect_args: every pointer / scalar of the header, in order, in the ctypes mirror."""
+    text = open(os.path.join(ROOT, "include", "ks_b200.h")).read()
+    body = re.search(r"typedef struct ks_collect_args \{(.*?)\} ks_collect_args;", text, flags=re.S).group(1)
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    names = []
+    for decl in body.split(";"):
+        decl = decl.strip()
+        if not decl:
+            continue
+        kind = "ptr" if "*" in decl else ("f32" if decl.startswith("float") else "i32")
+        for part in decl.split(","):
+            names.append((re.findall(r"(\w+)\s*$", part.strip())[0], kind))
+    ctype = {"ptr": ctypes.c_void_p, "f32": ctypes.c_float, "i32": ctypes.c_int32}
+    assert [(n, ctype[k]) for n, k in names] == list(_lib.KsCollectArgs._fields_)
+
+
 def good_config(**kw):
     F = np.zeros((4, 64), np.float32)
     c = dict(abi_version=2, num_envs=8, N=64, J=4, cfg_steps=250, max_episode_steps=400, burnin_periods=800,
