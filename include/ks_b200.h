@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define KS_ABI_VERSION 2
+#define KS_ABI_VERSION 3
 
 enum ks_precision { KS_F64 = 0, KS_F32 = 1 };
 /* KS_REWARD_L2: what the reference executes, -(1/N)*||u||^2 (kuramoto.py:64-65,72).
@@ -79,6 +79,10 @@ typedef struct ks_config {
                                   0 or 1 = full state (what the MBRL loop uses, mbrl.py:171,174) */
     int32_t solver;            /* enum ks_solver; 0 = the reference's FD-RK4 scheme */
     int32_t dealias;           /* KS_SOLVER_ETDRK4 only: 1 = 2/3-rule dealiasing of (u^2)_x, 0 = none */
+    int32_t env_index_base;    /* global index of this handle's env 0 (a sharded run: the shard's first env);
+                                  enters the Philox counter of device-drawn initial conditions so that a
+                                  sharded reset draws exactly what the single-GPU reset draws.  0 otherwise */
+    int32_t reserved0;         /* = 0 (keeps the doubles 8-byte aligned) */
     double L;                  /* domain length (22.0) */
     double dt;                 /* RK4 step (1e-3) */
     const float *forcing;      /* host, [J*N] row-major float32: GaussianForcing.forcing
@@ -155,14 +159,19 @@ int ks_out_layout(const ks_handle *h, size_t offsets[5], size_t *total);
  *   4. per period: ks_step_gather(h, actions_dev, &gathered, stream); `gathered` is a device
  *      pointer to [world][slot_bytes]: rank r's packed block at r*slot_bytes, valid (for work
  *      enqueued on `stream`) until the SECOND next ks_step_gather (double-buffered).
- * All ranks must call ks_step_gather the same number of times.  A peer that never signals makes
- * the handshake give up after ~2 s; ks_gather_status then reports timed_out = 1. */
+ * All ranks must call ks_step_gather the same number of times.  The handshake waits for every peer
+ * for up to KS_GATHER_TIMEOUT_S seconds (environment, default 120; ranks of a training job drift apart
+ * by seconds).  If a peer still has not signalled, the launch sets a sticky error word and poisons
+ * that peer's slot (its non-finite flags read 0xFF); every later ks_step_gather then FAILS with
+ * KS_ERR_STATE instead of handing out incomplete blocks, ks_gather_status reports timed_out = 1, and
+ * ks_gather_clear (after the application has re-synchronised its ranks) re-arms the exchange. */
 #define KS_MAX_WORLD 16
 #define KS_IPC_HANDLE_BYTES 64
 int ks_gather_init(ks_handle *h, int32_t world, int32_t rank, void *ipc_handle_out, size_t *slot_bytes);
 int ks_gather_connect(ks_handle *h, const void *all_handles);
 int ks_step_gather(ks_handle *h, const float *actions, void **gathered, void *stream);
 int ks_gather_status(ks_handle *h, int32_t *timed_out, void *stream);
+int ks_gather_clear(ks_handle *h, void *stream);
 
 /* One step of the reference's data-collection plumbing, fused (two small kernels), for stores of
  * length 1 as the MBRL loop uses them (mbrl.py:257-275): what StoreNObsVecWrapper.step_wait

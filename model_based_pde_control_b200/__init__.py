@@ -12,9 +12,12 @@ multi-GPU runs.  Importing it does not require a GPU; constructing an env does.
 from .device_pipeline import DeviceEnvPipeline, RolloutBatch, ScaleTransformDevice, SensorTransformDevice
 from .env import KSVecEnv
 from .forcing import GaussianForcing
-from .registration import ENV_ID, make, vector_make
+from .registration import ENV_ID, make, register, vector_make
 from .sharding import ShardedKSVecEnv, shard_range
+from .single_env import KSEnv
 
-__all__ = ["KSVecEnv", "GaussianForcing", "ENV_ID", "make", "vector_make", "ShardedKSVecEnv", "shard_range",
+__all__ = ["KSVecEnv", "KSEnv", "GaussianForcing", "ENV_ID", "make", "vector_make", "register", "ShardedKSVecEnv", "shard_range",
            "DeviceEnvPipeline", "RolloutBatch", "ScaleTransformDevice", "SensorTransformDevice"]
-__version__ = "0.1.0"
+__version__ = "0.2.0"
+
+register()      # no-op without gym; with gym the reference's env id resolves to the GPU env

@@ -12,7 +12,7 @@ import os
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG_DIR, "libks_b200.so")
 
-KS_ABI_VERSION = 2
+KS_ABI_VERSION = 3
 KS_F64, KS_F32 = 0, 1
 KS_REWARD_L2, KS_REWARD_DISSIPATION = 0, 1
 KS_HOST, KS_DEVICE = 0, 1
@@ -44,6 +44,8 @@ class KsConfig(ctypes.Structure):
         ("obs_stride", ctypes.c_int32),
         ("solver", ctypes.c_int32),
         ("dealias", ctypes.c_int32),
+        ("env_index_base", ctypes.c_int32),
+        ("reserved0", ctypes.c_int32),
         ("L", ctypes.c_double),
         ("dt", ctypes.c_double),
         ("forcing", ctypes.c_void_p),
@@ -84,6 +86,7 @@ EXPORTS = {
     "ks_gather_connect": (ctypes.c_int, [_vp, _vp]),
     "ks_step_gather": (ctypes.c_int, [_vp, _vp, ctypes.POINTER(_vp), _vp]),
     "ks_gather_status": (ctypes.c_int, [_vp, ctypes.POINTER(_i32), _vp]),
+    "ks_gather_clear": (ctypes.c_int, [_vp, _vp]),
     "ks_collect": (ctypes.c_int, [_vp, ctypes.POINTER(KsCollectArgs), _vp]),
     "ks_bench_fp64_peak": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                           ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]),

@@ -64,7 +64,9 @@ struct ks_handle {
     uint8_t *g_peer[KS_MAX_WORLD] = {nullptr};   // every rank's buffer as mapped into this process (own = g_buf)
     bool g_connected = false;
     uint32_t g_epoch = 0;
-    int32_t *g_timeout = nullptr;   // device flag set by the wait kernel when a peer never signalled
+    int32_t *g_timeout = nullptr;   // device: [2] spare words + the table of every rank's flag array
+    int32_t *g_timeout_host = nullptr;   // mapped pinned host word: 1 + rank of a peer that never signalled (sticky)
+    long long g_timeout_cycles = 0;
     size_t g_slot = 0, g_flags_off = 0, g_total = 0;
     int32_t *collect_keys = nullptr;   // [2 parities][2]: ordered-int min / max keys of ks_collect
     uint32_t collect_calls = 0;
@@ -218,7 +220,7 @@ __device__ inline void philox_round(uint32_t (&c)[4], uint32_t k0, uint32_t k1)
 template <typename T>
 __global__ void reset_rows(T *__restrict__ u, const double *__restrict__ u0, const uint8_t *__restrict__ mask,
                            uint8_t *__restrict__ nonfinite, int32_t *__restrict__ timestep, int zero_timestep, int B,
-                           int N, uint64_t seed)
+                           int N, uint64_t seed, uint32_t env_base)
 {
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (size_t)B * N) return;
@@ -227,7 +229,8 @@ __global__ void reset_rows(T *__restrict__ u, const double *__restrict__ u0, con
     if (u0 != nullptr) {
         u[idx] = (T)u0[idx];
     } else {
-        uint32_t c[4] = {pt, env, 0x4b53u /* 'KS' */, 0u};
+        // counter = (point, GLOBAL env index): a sharded run draws what the single-GPU run draws
+        uint32_t c[4] = {pt, env + env_base, 0x4b53u /* 'KS' */, 0u};
         uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
 #pragma unroll
         for (int r = 0; r < 10; ++r) {
@@ -301,9 +304,15 @@ __global__ void eval_rows(int M, int N, double dx, int reward_mode, const double
 // rank's epoch into peer r's flag word (a peer store, after a system-scope fence: the period
 // kernel that wrote the payload retired earlier on the same stream) and then waits until peer r's
 // epoch shows up in the local flag word.  Only the GPUs of DIFFERENT ranks ever wait on each other
-// here; the spin is bounded (~2 s of SM clocks) and reports through *timeout instead of hanging.
+// here.  The spin is bounded by `max_cycles` (KS_GATHER_TIMEOUT_S, default 120 s -- ranks of a real
+// training job drift apart by seconds: logging, checkpoints, evaluation passes); when the bound is
+// hit the launch does NOT pretend the block is complete: it sets the sticky *timeout word, which
+// lives in mapped host memory so that the next ks_step_gather / ks_gather_status sees it without a
+// synchronise and fails, and it poisons the missing peer's slot (non-finite flags = 0xFF) so that a
+// consumer that validates flags rejects the stale data even before the host has looked.
 __global__ void gather_signal_wait(uint32_t *const *peer_flags, volatile uint32_t *local_flags, int world, int rank,
-                                   uint32_t epoch, int32_t *timeout)
+                                   uint32_t epoch, volatile int32_t *timeout, long long max_cycles, uint8_t *poison_base,
+                                   size_t slot_bytes, size_t poison_off, int poison_len)
 {
     const int r = threadIdx.x;
     if (r >= world || r == rank) return;
@@ -311,8 +320,10 @@ __global__ void gather_signal_wait(uint32_t *const *peer_flags, volatile uint32_
     *reinterpret_cast<volatile uint32_t *>(peer_flags[r] + rank) = epoch;
     const long long t0 = clock64();
     while ((int32_t)(local_flags[r] - epoch) < 0) {
-        if (clock64() - t0 > 4000000000LL) {
-            atomicExch(timeout, 1);
+        if (clock64() - t0 > max_cycles) {
+            *timeout = 1 + r;
+            uint8_t *bad = poison_base + (size_t)r * slot_bytes + poison_off;
+            for (int i = 0; i < poison_len; ++i) bad[i] = 0xFF;
             break;
         }
         __nanosleep(64);
@@ -468,6 +479,7 @@ int ks_create(const ks_config *cfg, ks_handle **out)
                     cfg->num_envs, cfg->N, cfg->J, cfg->cfg_steps, cfg->L, cfg->dt);
     if (cfg->precision != KS_F64 && cfg->precision != KS_F32) return fail(nullptr, KS_ERR_ARG, "ks_create: bad precision");
     if (cfg->obs_stride < 0 || cfg->obs_stride > cfg->N) return fail(nullptr, KS_ERR_ARG, "ks_create: bad obs_stride");
+    if (cfg->env_index_base < 0) return fail(nullptr, KS_ERR_ARG, "ks_create: bad env_index_base");
     if (cfg->reward_mode != KS_REWARD_L2 && cfg->reward_mode != KS_REWARD_DISSIPATION)
         return fail(nullptr, KS_ERR_ARG, "ks_create: bad reward_mode");
 
@@ -605,6 +617,7 @@ int ks_destroy(ks_handle *h)
                 if (r != h->g_rank && h->g_peer[r]) cudaIpcCloseMemHandle(h->g_peer[r]);
         cudaFree(h->g_buf);
         cudaFree(h->g_timeout);
+        if (h->g_timeout_host) cudaFreeHost(h->g_timeout_host);
         cudaGetLastError();
     }
     delete h;
@@ -715,10 +728,10 @@ int ks_reset(ks_handle *h, const double *u0, const uint8_t *mask, int where, uin
     const unsigned blocks = (unsigned)((n + 255) / 256);
     if (h->cfg.precision == KS_F64)
         reset_rows<double><<<blocks, 256, 0, stream>>>((double *)h->u, u0_dev, mask_dev, h->nonfinite, h->timestep,
-                                                       K == 0, (int)B, h->cfg.N, seed);
+                                                       K == 0, (int)B, h->cfg.N, seed, (uint32_t)h->cfg.env_index_base);
     else
         reset_rows<float><<<blocks, 256, 0, stream>>>((float *)h->u, u0_dev, mask_dev, h->nonfinite, h->timestep,
-                                                      K == 0, (int)B, h->cfg.N, seed);
+                                                      K == 0, (int)B, h->cfg.N, seed, (uint32_t)h->cfg.env_index_base);
     KS_CUDA(h, cudaGetLastError());
     h->launches += 1;
     int rc = KS_OK;
@@ -847,6 +860,18 @@ int ks_gather_init(ks_handle *h, int32_t world, int32_t rank, void *ipc_handle_o
     KS_CUDA(h, cudaMemset(h->g_buf, 0, h->g_total));
     KS_CUDA(h, cudaMalloc(&h->g_timeout, 2 * sizeof(int32_t) + KS_MAX_WORLD * sizeof(void *)));
     KS_CUDA(h, cudaMemset(h->g_timeout, 0, 2 * sizeof(int32_t) + KS_MAX_WORLD * sizeof(void *)));
+    KS_CUDA(h, cudaHostAlloc((void **)&h->g_timeout_host, sizeof(int32_t), cudaHostAllocMapped));
+    *h->g_timeout_host = 0;
+    {
+        double seconds = 120.0;
+        if (const char *e = getenv("KS_GATHER_TIMEOUT_S")) {
+            const double v = atof(e);
+            if (v > 0.0) seconds = v;
+        }
+        int khz = 1965000;
+        cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, h->cfg.device);
+        h->g_timeout_cycles = (long long)(seconds * 1e3 * (double)khz);
+    }
     KS_CUDA(h, cudaDeviceSynchronize());
     cudaIpcMemHandle_t hd;
     KS_CUDA(h, cudaIpcGetMemHandle(&hd, h->g_buf));
@@ -875,6 +900,7 @@ int ks_gather_connect(ks_handle *h, const void *all_handles)
     uint32_t *flags[KS_MAX_WORLD] = {nullptr};
     for (int r = 0; r < h->g_world; ++r) flags[r] = reinterpret_cast<uint32_t *>(h->g_peer[r] + h->g_flags_off);
     KS_CUDA(h, cudaMemcpy(h->g_timeout + 2, flags, sizeof(flags), cudaMemcpyHostToDevice));
+    *h->g_timeout_host = 0;      // (re-)arm
     h->g_connected = true;
     return KS_OK;
 }
@@ -884,6 +910,11 @@ int ks_step_gather(ks_handle *h, const float *actions, void **gathered, void *st
     if (!h || !actions) return h ? fail(h, KS_ERR_ARG, "ks_step_gather: NULL argument") : KS_ERR_ARG;
     if (!h->g_buf || (h->g_world > 1 && !h->g_connected))
         return fail(h, KS_ERR_STATE, "ks_step_gather: gather not initialised / connected");
+    if (h->g_timeout_host && *(volatile int32_t *)h->g_timeout_host != 0)
+        return fail(h, KS_ERR_STATE,
+                    "ks_step_gather: rank %d never signalled an earlier exchange within the handshake bound "
+                    "(KS_GATHER_TIMEOUT_S); the gathered blocks since then are incomplete -- ks_gather_clear re-arms",
+                    *(volatile int32_t *)h->g_timeout_host - 1);
     cudaStream_t stream = (cudaStream_t)stream_;
     DeviceGuard guard(h->cfg.device);
     h->g_epoch += 1;
@@ -903,7 +934,8 @@ int ks_step_gather(ks_handle *h, const float *actions, void **gathered, void *st
     if (h->g_world > 1) {
         gather_signal_wait<<<1, 32, 0, stream>>>(reinterpret_cast<uint32_t *const *>(h->g_timeout + 2),
                                                  reinterpret_cast<volatile uint32_t *>(h->g_buf + h->g_flags_off), h->g_world,
-                                                 h->g_rank, h->g_epoch, h->g_timeout);
+                                                 h->g_rank, h->g_epoch, h->g_timeout_host, h->g_timeout_cycles,
+                                                 h->g_buf + parity_off, h->g_slot, h->out_off[4], h->cfg.num_envs);
         KS_CUDA(h, cudaGetLastError());
         h->launches += 1;
     }
@@ -914,10 +946,20 @@ int ks_step_gather(ks_handle *h, const float *actions, void **gathered, void *st
 int ks_gather_status(ks_handle *h, int32_t *timed_out, void *stream_)
 {
     if (!h || !timed_out) return KS_ERR_ARG;
-    if (!h->g_timeout) return fail(h, KS_ERR_STATE, "ks_gather_status: gather not initialised");
+    if (!h->g_timeout_host) return fail(h, KS_ERR_STATE, "ks_gather_status: gather not initialised");
     DeviceGuard guard(h->cfg.device);
-    KS_CUDA(h, cudaMemcpyAsync(timed_out, h->g_timeout, sizeof(int32_t), cudaMemcpyDeviceToHost, (cudaStream_t)stream_));
     KS_CUDA(h, cudaStreamSynchronize((cudaStream_t)stream_));
+    *timed_out = *(volatile int32_t *)h->g_timeout_host != 0 ? 1 : 0;
+    return KS_OK;
+}
+
+int ks_gather_clear(ks_handle *h, void *stream_)
+{
+    if (!h) return KS_ERR_ARG;
+    if (!h->g_timeout_host) return fail(h, KS_ERR_STATE, "ks_gather_clear: gather not initialised");
+    DeviceGuard guard(h->cfg.device);
+    KS_CUDA(h, cudaStreamSynchronize((cudaStream_t)stream_));
+    *h->g_timeout_host = 0;
     return KS_OK;
 }
 

@@ -69,6 +69,9 @@ class KSVecEnv(VectorEnvBase):
                       period at the default grid); ``dt`` / ``cfg_steps`` are then the ETDRK4 step
                       and the steps per period, e.g. ``dt=0.025, cfg_steps=10`` for the reference's
                       0.25 time units per control period.  ``dealias`` = 2/3 rule on ``(u^2)_x``.
+    ``env_index_base`` global index of this env's member 0 (a shard of a larger batch): enters the counter of
+                      the device generator, so that ``reset_device(seed)`` of a sharded run draws the initial
+                      conditions the single-GPU run draws, whatever the GPU count.
     ``sensor_stride`` observation sampling fused into the kernel's output stage: observations are
                       ``u[..., stride//2::stride]`` as ``SensorTransform(stride)`` would return
                       (``pdegym/common/transforms.py:231-247``); 1 = full state, which is what the
@@ -83,7 +86,7 @@ class KSVecEnv(VectorEnvBase):
                  device: Optional[int] = None, precision: str = "f64", reward_mode: Optional[str] = None,
                  ic: str = "numpy", burnin_periods: Optional[int] = None, points_per_lane: int = 0,
                  sensor_stride: int = 1, copy: bool = True, reset_mode: str = "burnin", pool_slots: int = 2,
-                 solver: str = "fd_rk4", dealias: bool = True, **kwargs):
+                 solver: str = "fd_rk4", dealias: bool = True, env_index_base: int = 0, **kwargs):
         cfg = dict(config or {})
         cfg.update(kwargs)
         self.L = float(cfg.pop("L", 22.0))
@@ -114,6 +117,7 @@ class KSVecEnv(VectorEnvBase):
         if reset_mode not in ("burnin", "pool"):
             raise ValueError("reset_mode must be 'burnin' or 'pool'")
         self.reset_mode, self._pool_slots, self._pool = reset_mode, int(pool_slots), None
+        self.points_per_lane_request, self.env_index_base = int(points_per_lane), int(env_index_base)
         self.sensor_stride = int(sensor_stride)
         if not (1 <= self.sensor_stride <= self.N):
             raise ValueError("sensor_stride must be in [1, N]")
@@ -146,7 +150,8 @@ class KSVecEnv(VectorEnvBase):
             max_episode_steps=self.max_episode_steps, burnin_periods=self.burnin_periods,
             precision=_lib.PRECISIONS[precision], reward_mode=_lib.REWARD_MODES[reward_mode],
             device=self.device_index, points_per_lane=points_per_lane, obs_stride=self.sensor_stride,
-            solver=_lib.SOLVERS[solver], dealias=int(self.dealias), L=self.L, dt=self.dt,
+            solver=_lib.SOLVERS[solver], dealias=int(self.dealias), env_index_base=self.env_index_base, reserved0=0,
+            L=self.L, dt=self.dt,
             forcing=self._F_host.ctypes.data)
         handle = ctypes.c_void_p()
         torch.cuda.init()
@@ -167,7 +172,7 @@ class KSVecEnv(VectorEnvBase):
         self._act_pinned = torch.empty((B, self.J), dtype=torch.float32, pin_memory=True)
         self._h_act = self._act_pinned.numpy()
         # device-side outputs of the tensor API (allocated on first use)
-        self._d_out = None
+        self._d_out = {}
         self._gather = None
         self._pending_actions = None
         self.h2d_bytes_per_step = B * self.J * 4
@@ -248,11 +253,14 @@ class KSVecEnv(VectorEnvBase):
         """Host draws of ``reset``'s initial condition: env ``i`` uses the legacy MT19937 stream of
         ``np.random.seed(seed + i)`` (gym 0.25.2 seeds sub-env ``i`` with ``seed + i``), then
         ``uniform(-0.4, 0.4, N)`` (kuramoto.py:101,106)."""
+        # One MT19937 key schedule per env is what the seeded-parity contract costs (init_genrand + 624-word
+        # twist: ~6 us per env, 0.4 s at 65 536 envs); ``reset(seed=None)`` / ``ic="device"`` / auto-resets
+        # never come here.  The generator object is re-seeded in place instead of rebuilt per env.
         u0 = np.zeros((self.num_envs, self.N), dtype=np.float64)
-        for i in range(self.num_envs):
-            if mask is not None and not mask[i]:
-                continue
-            rs = np.random.RandomState(None if seed is None else seed + i)
+        rs = np.random.RandomState(0)
+        rows = range(self.num_envs) if mask is None else np.nonzero(np.asarray(mask))[0]
+        for i in rows:
+            rs.seed(None if seed is None else seed + int(i))
             u0[i] = rs.uniform(-IC_AMPLITUDE, IC_AMPLITUDE, size=self.N)
         return u0
 
@@ -346,16 +354,29 @@ class KSVecEnv(VectorEnvBase):
         infos = {"step": steps, "_step": np.ones(self.num_envs, dtype=bool)}
         if truncated.any():
             # gym 0.25.2 vector-env auto-reset: final obs is the single env's float64 (1,N) array
+            # (the float64 state has to be fetched for that: the packed block carries float32 observations)
             u, _ = self.get_state()
-            finals = np.empty(self.num_envs, dtype=object)
-            for i in np.nonzero(truncated)[0]:
-                finals[i] = u[i, self.sensor_stride // 2::self.sensor_stride].reshape(1, self.obs_len)
+            finals_block = np.ascontiguousarray(u[:, self.sensor_stride // 2::self.sensor_stride]).reshape(
+                self.num_envs, 1, self.obs_len)
+            finals = np.fromiter(iter(finals_block), dtype=object, count=self.num_envs)   # (1,No) views of ONE block
+            idx = np.nonzero(truncated)[0]
+            if idx.size != self.num_envs:
+                finals[~truncated] = None
             infos["final_observation"] = finals
             infos["_final_observation"] = truncated.copy()
             self._auto_reset(None if truncated.all() else truncated)
-            u_new, _ = self.get_state()
+            # post-reset observations: float32 on the device, only the reset rows cross PCIe
+            u_dev, _ = self.get_state_device()
+            o_dev = u_dev[:, self.sensor_stride // 2::self.sensor_stride].to(torch.float32)
             obs = np.array(obs)
-            obs[truncated] = self._observe(u_new[truncated])
+            if truncated.all():
+                new = o_dev.cpu().numpy()
+                self._raise_if_nonfinite(new)
+                obs[:, 0] = new
+            else:
+                new = o_dev[torch.as_tensor(idx, device=self.device)].cpu().numpy()
+                self._raise_if_nonfinite(new)
+                obs[idx, 0] = new
         return obs, rewards, terminated, truncated, infos
 
     def step(self, actions):
@@ -418,8 +439,11 @@ class KSVecEnv(VectorEnvBase):
         """Output tensors of the device API.  For a single period (K = 0) all five are typed views
         into ONE contiguous byte block with the layout of ``ks_out_layout`` -- a sharded run
         all-gathers that block with a single collective (``sharding.gather_packed``)."""
-        key = K
-        if self._d_out is None or self._d_out[0] != key:
+        out = self._d_out.get(K)
+        if out is None:
+            # The single-period block (K = 0) lives as long as the env: CUDA graphs captured by
+            # ``DeviceEnvPipeline.rollout_graphed`` and the fused gather have its raw pointers baked in.
+            # Rollout buffers are kept for the most recent K only.
             B, dev = self.num_envs, self.device
             if K == 0:
                 offs, total = self._out_offsets, self.d2h_bytes_per_step
@@ -440,8 +464,10 @@ class KSVecEnv(VectorEnvBase):
                            truncated=torch.empty(lead, dtype=torch.uint8, device=dev),
                            step=torch.empty(lead, dtype=torch.int32, device=dev),
                            nonfinite=torch.empty(lead, dtype=torch.uint8, device=dev))
-            self._d_out = (key, out)
-        return self._d_out[1]
+            for old in [k for k in self._d_out if k != 0]:
+                del self._d_out[old]
+            self._d_out[K] = out
+        return out
 
     def packed_fields(self) -> dict:
         """``{name: (byte offset, torch dtype, per-env shape)}`` of the packed single-period block."""
@@ -519,6 +545,7 @@ class KSVecEnv(VectorEnvBase):
             raise RuntimeError("step_gather() before gather_init() / gather_connect()")
         a = actions.to(device=self.device, dtype=torch.float32).reshape(self.num_envs, self.J).contiguous()
         ptr = ctypes.c_void_p()
+        # fails (KsError, KS_ERR_STATE) once an earlier exchange timed out: never hands out incomplete blocks
         _lib.check(self._h, self._lib.ks_step_gather(self._h, _ptr(a), ctypes.byref(ptr), self._stream()))
         g = self._gather
         views = g["views"].get(ptr.value)
@@ -545,6 +572,10 @@ class KSVecEnv(VectorEnvBase):
         flag = ctypes.c_int32()
         _lib.check(self._h, self._lib.ks_gather_status(self._h, ctypes.byref(flag), self._stream()))
         return bool(flag.value)
+
+    def gather_clear(self) -> None:
+        """Re-arm the fused exchange after a time-out (the application has re-synchronised its ranks)."""
+        _lib.check(self._h, self._lib.ks_gather_clear(self._h, self._stream()))
 
     def rollout_device(self, actions: Optional[torch.Tensor], K: Optional[int] = None, outputs: bool = True) -> dict:
         """``K`` control periods in ONE persistent launch (open loop).  ``actions``: CUDA float32

@@ -29,14 +29,22 @@ class ResetPool:
     def __init__(self, env, slots: int = 2, seed: Optional[int] = None):
         from .env import KSVecEnv
 
-        cfg = dict(L=env.L, N=env.N, cfg_steps=env.cfg_steps, Tmax=env.Tmax, dt=env.dt, sigma=env.sigma)
+        # the burner is the parent's twin: same discretisation (solver, dealiasing, dt), same layout
+        cfg = dict(L=env.L, N=env.N, cfg_steps=env.cfg_steps, Tmax=env.Tmax, dt=env.dt, sigma=env.sigma,
+                   objective=env.objective)
         self.device = env.device
         self.burner = KSVecEnv(env.num_envs, cfg, Xi=env.Xi, device=env.device_index, precision=env.precision,
-                               reward_mode=env.reward_mode, ic="device", burnin_periods=env.burnin_periods)
+                               reward_mode=env.reward_mode, ic="device", burnin_periods=env.burnin_periods,
+                               solver=env.solver, dealias=env.dealias, sensor_stride=env.sensor_stride,
+                               points_per_lane=env.points_per_lane_request, env_index_base=env.env_index_base)
         lo, _hi = torch.cuda.Stream.priority_range()          # lo = least urgent
         self.stream = torch.cuda.Stream(device=self.device, priority=lo)
         self.slots = [torch.empty((env.num_envs, env.N), dtype=torch.float64, device=self.device) for _ in range(slots)]
         self.ready = [torch.cuda.Event() for _ in range(slots)]
+        # per slot: did any burned-in state leave the finite range?  Written on the side stream after the
+        # burn-in, copied to pinned host memory, read when the slot is taken (after its ready event).
+        self.bad_dev = [torch.zeros(1, dtype=torch.uint8, device=self.device) for _ in range(slots)]
+        self.bad_host = [torch.zeros(1, dtype=torch.uint8).pin_memory() for _ in range(slots)]
         self.consumed = [None] * slots
         self._next_seed = int.from_bytes(os.urandom(8), "little") if seed is None else int(seed)
         self._head = 0
@@ -51,6 +59,8 @@ class ResetPool:
             self.burner.reset_device(seed=self._next_seed)    # IC + burn-in, ONE launch, on the side stream
             u, _ = self.burner.get_state_device()
             self.slots[i].copy_(u)
+            self.bad_dev[i].copy_((~torch.isfinite(u)).any().to(torch.uint8).reshape(1))
+            self.bad_host[i].copy_(self.bad_dev[i], non_blocking=True)
             self.ready[i].record(self.stream)
         self._next_seed = (self._next_seed + 0x9E3779B97F4A7C15) & (2 ** 64 - 1)
         self.refills += 1
@@ -61,6 +71,12 @@ class ResetPool:
         self._head = (self._head + 1) % len(self.slots)
         cur = torch.cuda.current_stream(self.device)
         cur.wait_event(self.ready[i])
+        # The flag is one pinned byte written before the ready event; the refill was issued a whole
+        # episode ago, so this wait is normally free.
+        self.ready[i].synchronize()
+        if int(self.bad_host[i][0]) != 0:
+            raise FloatingPointError("reset pool: a burned-in state left the finite range (overflow in the burn-in "
+                                     "launch; np.seterr(over='raise') in the reference)")
         return self.slots[i], i
 
     def release(self, i: int) -> None:

@@ -127,7 +127,9 @@ class ShardedKSVecEnv:
         if env_factory is None:
             from .env import KSVecEnv
 
-            env_factory = lambda n: KSVecEnv(n, config, **kwargs)  # noqa: E731
+            # env_index_base: the device generator's counter uses the GLOBAL env index, so a sharded
+            # reset_device(seed) equals the single-GPU one whatever the world size
+            env_factory = lambda n: KSVecEnv(n, config, env_index_base=self.lo, **kwargs)  # noqa: E731
         self.local = env_factory(self.hi - self.lo)
         self._fused = False
 
@@ -151,7 +153,9 @@ class ShardedKSVecEnv:
         ``gather="fused"`` returns the same views filled by the kernel epilogues themselves
         (peer stores over NVLink + epoch handshake, ``ks_step_gather``) -- no NCCL call per period."""
         if gather == "fused" and self.world_size > 1:
-            # kernel epilogue stores straight into every peer's buffer over NVLink (no collective call)
+            # kernel epilogue stores straight into every peer's buffer over NVLink (no collective call).
+            # A peer that did not arrive within KS_GATHER_TIMEOUT_S makes the NEXT call raise KsError (the
+            # handshake kernel poisons the incomplete block and sets a host-visible sticky word).
             if not self._fused:
                 connect_fused_gather(self.local, self.group)
                 self._fused = True
@@ -159,15 +163,27 @@ class ShardedKSVecEnv:
         out = self.local.step_device(self.local_slice(actions.reshape(self.num_envs, -1)))
         if not gather:
             return out
-        if gather == "packed" and self.world_size > 1:
-            return gather_packed(out["packed"], self.local.packed_fields(), self.local_num_envs, self.group)
+        if gather in ("packed", "fused"):
+            if self.world_size > 1:
+                return gather_packed(out["packed"], self.local.packed_fields(), self.local_num_envs, self.group)
+            # world of one: the same [world, local_envs, ...] view shape as the multi-rank paths
+            return {k: v.unsqueeze(0) for k, v in out.items()}
         out = {k: v for k, v in out.items() if k != "packed"}
         return self.gather(out)
 
     def reset_device(self, seed: Optional[int] = None, **kwargs) -> None:
-        # distinct Philox streams per rank: env index inside the key is local, so offset the seed
-        s = None if seed is None else seed + 0x9E3779B97F4A7C15 * self.rank
-        self.local.reset_device(seed=s, **kwargs)
+        """Device-drawn initial conditions + burn-in on every shard.  The generator is keyed by (seed;
+        point, GLOBAL env index), so with one shared ``seed`` the batch equals the single-GPU
+        ``reset_device(seed)`` bit for bit, for every world size.  ``seed=None``: rank 0 draws one from the
+        OS and broadcasts it."""
+        if seed is None:
+            import os
+
+            box = [int.from_bytes(os.urandom(8), "little")]
+            if self.world_size > 1:
+                dist.broadcast_object_list(box, src=0, group=self.group)
+            seed = box[0]
+        self.local.reset_device(seed=seed, **kwargs)
 
     def set_state(self, u_full, timestep_full=None) -> None:
         ts = None if timestep_full is None else timestep_full[self.lo:self.hi]

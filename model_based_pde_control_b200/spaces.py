@@ -11,6 +11,7 @@ try:  # pragma: no cover - depends on the environment
     from gym.spaces import Box  # type: ignore
     from gym.vector import VectorEnv as _GymVectorEnv  # type: ignore
 
+    _GymEnv = _gym.Env
     HAVE_GYM = True
 except Exception:  # ImportError or a broken install
     _gym = None
@@ -46,6 +47,18 @@ except Exception:  # ImportError or a broken install
         def __repr__(self):
             return f"Box({self.low.min()}, {self.high.max()}, {self.shape}, {self.dtype})"
 
+    class _GymEnv:  # type: ignore[no-redef]
+        """Protocol base: the subset of ``gym.Env`` the reference relies on."""
+
+        metadata: dict = {}
+
+        @property
+        def unwrapped(self):
+            return self
+
+        def close(self):
+            pass
+
     class _GymVectorEnv:  # type: ignore[no-redef]
         """Protocol base: the subset of ``gym.vector.VectorEnv`` the reference relies on."""
 
@@ -76,6 +89,7 @@ except Exception:  # ImportError or a broken install
 
 
 VectorEnvBase = _GymVectorEnv
+EnvBase = _GymEnv
 
 
 def batch_space(space, n: int):

@@ -4,7 +4,8 @@ Only ``tests/``, ``tests/golden/make_golden.py`` and ``oracle/`` self-checks may
 Nothing on the product path (``model_based_pde_control_b200``) may import anything under
 ``oracle/``.
 
-The reference (``/root/reference``, read-only, present in the build container only) cannot be
+The reference (``/root/reference``, read-only, present in the build container only; installed
+byte-identically into ``baseline/_ref`` by ``oracle/install_ref.py`` so that it travels to the GPU box) cannot be
 imported as-is:
 
 * ``pdegym/__init__.py:2`` imports a ``pdegym.burgers`` package that is not in the tree
@@ -27,8 +28,13 @@ import types
 
 import numpy as np
 
+_REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+# Search order: an explicit override, the install that travels to the GPU box
+# (``baseline/_ref``, made by ``oracle/install_ref.py``: byte-identical .py files), the build
+# container's read-only tree.
 REFERENCE_ROOTS = (
     os.environ.get("KS_REFERENCE_ROOT", ""),
+    os.path.join(_REPO, "baseline", "_ref"),
     "/root/reference",
 )
 
@@ -211,6 +217,41 @@ def load_reference_wrappers():
         sys.modules["pdegym.common.vec_wrappers"] = mod
         spec.loader.exec_module(mod)
     return sys.modules["pdegym.common.vec_wrappers"], transforms
+
+
+def load_reference_worker():
+    """``(worker module, replay module)``: the reference's data-collection loop
+    (``pdecontrol/mbrl/worker.py:39-93``) and its replay container, executed where they lie.
+    ``worker.py`` imports two modules only for type annotations -- ``pdecontrol.mbrl.callbacks`` (pulls in
+    wandb / matplotlib / seaborn) and ``pdecontrol.mbrl.world.wrappers`` (pulls in the surrogate models);
+    those two get attribute-only stand-ins, ``Worker`` / ``PDEEnvStack`` / ``ExperienceReplay`` / ``Sample``
+    are the reference's own code."""
+    load_reference_wrappers()
+    import importlib.util
+
+    root = reference_root()
+    for name, attr in (("pdecontrol.mbrl.callbacks", "PDECallback"),
+                       ("pdecontrol.mbrl.world", None),
+                       ("pdecontrol.mbrl.world.wrappers", "BaseWorldVecEnvWrapper")):
+        if name not in sys.modules:
+            mod = types.ModuleType(name)
+            if attr is None:
+                mod.__path__ = []
+            else:
+                setattr(mod, attr, type(attr, (), {}))
+            sys.modules[name] = mod
+
+    def _load(name, relpath):
+        if name not in sys.modules:
+            spec = importlib.util.spec_from_file_location(name, os.path.join(root, relpath))
+            mod = importlib.util.module_from_spec(spec)
+            sys.modules[name] = mod
+            spec.loader.exec_module(mod)
+        return sys.modules[name]
+
+    replay = _load("pdecontrol.mbrl.replay", "pdecontrol/mbrl/replay.py")
+    worker = _load("pdecontrol.mbrl.worker", "pdecontrol/mbrl/worker.py")
+    return worker, replay
 
 
 def make_reference_env(Xi=None, **config):

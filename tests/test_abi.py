@@ -26,7 +26,7 @@ def test_header_symbols_all_exported_and_bound():
         assert hasattr(lib, name), f"{name} declared in ks_b200.h but not exported by libks_b200.so"
         assert name in _lib.EXPORTS, f"{name} has no ctypes prototype in _lib.EXPORTS"
     assert set(_lib.EXPORTS) == set(syms)
-    assert lib.ks_abi_version() == _lib.KS_ABI_VERSION == 2
+    assert lib.ks_abi_version() == _lib.KS_ABI_VERSION == 3
 
 
 def test_config_struct_layout_matches_header():
@@ -37,7 +37,7 @@ def test_config_struct_layout_matches_header():
     fields = re.findall(r"(int32_t|double|const float \*)\s*(\w+);", body)
     ctype = {"int32_t": ctypes.c_int32, "double": ctypes.c_double, "const float *": ctypes.c_void_p}
     assert [(n, ctype[t]) for t, n in fields] == list(_lib.KsConfig._fields_)
-    assert ctypes.sizeof(_lib.KsConfig) == 14 * 4 + 2 * 8 + 8
+    assert ctypes.sizeof(_lib.KsConfig) == 16 * 4 + 2 * 8 + 8
 
 
 def test_collect_args_struct_layout_matches_header():
@@ -59,7 +59,7 @@ def test_collect_args_struct_layout_matches_header():
 
 def good_config(**kw):
     F = np.zeros((4, 64), np.float32)
-    c = dict(abi_version=2, num_envs=8, N=64, J=4, cfg_steps=250, max_episode_steps=400, burnin_periods=800,
+    c = dict(abi_version=3, num_envs=8, N=64, J=4, cfg_steps=250, max_episode_steps=400, burnin_periods=800,
              precision=0, reward_mode=0, device=0, points_per_lane=0, obs_stride=1, L=22.0, dt=1e-3,
              forcing=F.ctypes.data)
     c.update(kw)

@@ -174,7 +174,7 @@ def test_sensor_stride_matches_sensor_transform(stride):
 
 
 def test_spaces_attributes_and_controller_surface():
-    from model_based_pde_control_b200 import KSVecEnv, make, vector_make
+    from model_based_pde_control_b200 import KSVecEnv, vector_make
 
     env = vector_make("KuramotoSivashinskyEnv-v0", num_envs=3)
     assert isinstance(env, KSVecEnv) and env.num_envs == 3
@@ -189,7 +189,7 @@ def test_spaces_attributes_and_controller_surface():
     assert sc["noise"] == 0.1 and sc["lmbda"] == 1.0 and sc["Xi"] == [0.0, 0.25, 0.5, 0.75] and sc["objective"] == "dissipation"
     env.set_state(np.zeros((3, 64)), [0, 4, 400])
     assert np.allclose(env.time, np.array([0, 4, 400]) * 250 * 0.001)
-    big = make({"L": 88.0, "N": 256}, num_envs=2, Xi=[k / 8 for k in range(8)])
+    big = vector_make("KuramotoSivashinskyEnv-v0", num_envs=2, config={"L": 88.0, "N": 256}, Xi=[k / 8 for k in range(8)])
     assert big.single_action_space.shape == (1, 8) and big.launch_info()["lanes_per_env"] in (16, 32)
     env.close(); big.close()
 

@@ -70,7 +70,59 @@ def test_package_surface_and_factories_fail_loudly_without_cuda():
         pkg.KSVecEnv(2, precision="bf16")
     if not torch.cuda.is_available():
         with pytest.raises(RuntimeError, match="no CPU fallback"):
-            pkg.make({}, num_envs=4)
+            pkg.make({})
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            pkg.vector_make(pkg.ENV_ID, num_envs=4)
+
+
+def test_register_uses_the_references_id_and_keywords(monkeypatch):
+    """``register()`` = ``gym.envs.register(id="KuramotoSivashinskyEnv-v0", entry_point=..., order_enforce=False,
+    new_step_api=True)`` as ``pdegym/kuramoto/__init__.py:26-31`` does; a no-op (False) without gym."""
+    import sys
+    import types
+    from model_based_pde_control_b200 import registration
+
+    if not registration.HAVE_GYM:
+        assert registration.register() is False
+    calls = []
+    gym = types.ModuleType("gym")
+    gym.envs = types.SimpleNamespace(registry={}, register=lambda **kw: calls.append(kw))
+    monkeypatch.setitem(sys.modules, "gym", gym)
+    monkeypatch.setattr(registration, "HAVE_GYM", True)
+    assert registration.register() is True
+    assert calls == [dict(id="KuramotoSivashinskyEnv-v0", entry_point="model_based_pde_control_b200.registration:make",
+                          order_enforce=False, new_step_api=True)]
+    gym.envs.registry[registration.ENV_ID] = object()          # e.g. pdegym was imported first
+    assert registration.register() is False and len(calls) == 1
+    assert registration.register(force=True) is True and len(calls) == 2
+    mod, fn = registration.ENTRY_POINT.split(":")
+    assert getattr(sys.modules[mod], fn) is registration.make
+
+
+def test_local_time_limit_wrapper():
+    from model_based_pde_control_b200.single_env import TimeLimit
+
+    class Inner:
+        observation_space = action_space = None
+        metadata, reward_range, marker = {}, (0, 1), 7
+        unwrapped = property(lambda self: self)
+
+        def reset(self, **kw):
+            return "obs"
+
+        def step(self, a):
+            return "obs", 1.0, False, False, {}
+
+        def close(self):
+            return "closed"
+
+    env = TimeLimit(Inner(), 3)
+    assert env.reset() == "obs" and env.marker == 7 and env.unwrapped is env.env
+    assert [env.step(0)[3] for _ in range(4)] == [False, False, True, True]
+    env.reset()
+    assert env.step(0)[3] is False and env.close() == "closed"
+    with pytest.raises(ValueError):
+        TimeLimit(Inner(), 3, new_step_api=False)
 
 
 def test_product_package_never_imports_the_oracle():
