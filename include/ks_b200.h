@@ -224,6 +224,8 @@ int ks_eval(ks_handle *h, int32_t M, const double *u, const float *phi, double *
  * a register-resident DFMA loop, best and mean over `repeats` launches of `iters` iterations x 16
  * independent chains per thread.  Used by bench.py as the self-measured FP64 roofline peak. */
 int ks_bench_fp64_peak(int device, int iters, int repeats, double *tflops_best, double *tflops_mean);
+/* The same with FFMA: the roofline denominator of the optional fp32 mode. */
+int ks_bench_fp32_peak(int device, int iters, int repeats, double *tflops_best, double *tflops_mean);
 
 /* Introspection */
 int ks_get_config(const ks_handle *h, ks_config *out); /* forcing pointer is returned NULL */

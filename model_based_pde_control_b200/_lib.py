@@ -10,7 +10,8 @@ import ctypes
 import os
 
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG_DIR, "libks_b200.so")
+# KS_LIB_PATH: development override (tools/sweep.py times experimental builds of the same ABI side by side)
+LIB_PATH = os.environ.get("KS_LIB_PATH") or os.path.join(_PKG_DIR, "libks_b200.so")
 
 KS_ABI_VERSION = 3
 KS_F64, KS_F32 = 0, 1
@@ -89,6 +90,8 @@ EXPORTS = {
     "ks_gather_clear": (ctypes.c_int, [_vp, _vp]),
     "ks_collect": (ctypes.c_int, [_vp, ctypes.POINTER(KsCollectArgs), _vp]),
     "ks_bench_fp64_peak": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                          ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]),
+    "ks_bench_fp32_peak": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                           ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]),
 }
 

@@ -264,6 +264,10 @@ __device__ __forceinline__ void rk4_stage(T (&u)[P], T (&us)[P], T (&acc)[P], co
         // chain simply continues from `lin`)
         constexpr bool kSplit = (STAGE == 0 && RMODE == kRewardDissipation);
         const bool neg = is_negative(h[m]);
+        // (computing BOTH one-sided chains on the FP64 pipe and selecting the result -- 10 DFMA + 2 SEL per
+        // point instead of 5 DFMA + 9 SEL, in point order or in scatter order -- was measured in round 2:
+        // 0.4108 / 0.4091 ms against 0.4023 ms per period at 4096 envs, 5.60 / 5.59 against 5.42 ms at
+        // 65 536; profiles/round2_sweep_upwind_variants.jsonl)
         T t[5];
         if constexpr (sizeof(T) == 8) {
             t[0] = select_signed(neg, qlo[m], qhi[m], qlo[m], nqhi[m]);

@@ -87,19 +87,40 @@ def test_fp32_mode_statistics():
     assert abs(diss - float(g["dissipation"])) <= TOL * abs(float(g["dissipation"]))
 
 
-def test_spectral_solver_statistics_vs_its_oracle():
+def test_fp32_mode_statistics_large_domain():
+    """BASELINE configs[3] in the optional fp32 mode: N=256, L=88, 8 jets against the reference-scheme
+    fixture (1024 reference episodes; per bin 1 % or 4 standard errors of the fixture, whichever is
+    larger -- the same widening as the fp64 test above; the totals strictly 1 %)."""
+    if not os.path.exists(os.path.join(GOLDEN, "stats_large.npz")):
+        pytest.skip("stats_large.npz not generated")
+    g, spec, diss, u2, rew = gpu_statistics("large", 4096, precision="f32")
+    ref = g["spectrum"]
+    big = ref > 0.01 * ref.sum()
+    rel = np.abs(spec[big] - ref[big]) / ref[big]
+    tol = np.maximum(TOL, 4.0 * g["spectrum_sem"][big] / ref[big])
+    print(f"large fp32: spectrum rel. dev {np.round(rel, 4).tolist()}; dissipation {diss:.5f} vs {float(g['dissipation']):.5f}; "
+          f"mean u^2 {u2:.5f} vs {float(g['mean_u2']):.5f}")
+    assert (rel <= tol).all(), (rel / tol).max()
+    assert abs(spec[big].sum() / ref[big].sum() - 1) <= TOL
+    assert abs(diss - float(g["dissipation"])) <= TOL * abs(float(g["dissipation"]))
+    assert abs(u2 - float(g["mean_u2"])) <= TOL * float(g["mean_u2"])
+    assert abs(rew - float(g["mean_reward"])) <= TOL * abs(float(g["mean_reward"]))
+
+
+@pytest.mark.parametrize("name,B", [("spectral_default", 32768), ("spectral_large", 8192)])
+def test_spectral_solver_statistics_vs_its_oracle(name, B):
     """The ETDRK4 solver against the statistics of its own NumPy oracle (tests/golden/
     make_stats_spectral.py; the reference has no spectral solver).  Same 1 % gate, widened only by
     the fixture's recorded standard error where that is larger (the unforced mean mode performs a
     random walk under the jets' mean forcing, so bin 0 is noisy)."""
-    if not os.path.exists(os.path.join(GOLDEN, "stats_spectral_default.npz")):
-        pytest.skip("stats_spectral_default.npz not generated")
-    g, spec, diss, u2, rew = gpu_statistics("spectral_default", 32768, solver="etdrk4")
+    if not os.path.exists(os.path.join(GOLDEN, f"stats_{name}.npz")):
+        pytest.skip(f"stats_{name}.npz not generated")
+    g, spec, diss, u2, rew = gpu_statistics(name, B, solver="etdrk4")
     ref, sem = g["spectrum"], g["spectrum_sem"]
     big = ref > 0.01 * ref.sum()
     tol = np.maximum(TOL * ref[big], 4.0 * sem[big])
     dev = np.abs(spec[big] - ref[big])
-    print(f"spectral: spectrum rel. dev {np.round(dev / ref[big], 4).tolist()} (tol {np.round(tol / ref[big], 4).tolist()}); "
+    print(f"{name}: spectrum rel. dev {np.round(dev / ref[big], 4).tolist()} (tol {np.round(tol / ref[big], 4).tolist()}); "
           f"dissipation {diss:.5f} vs {float(g['dissipation']):.5f}; mean u^2 {u2:.5f} vs {float(g['mean_u2']):.5f}")
     assert (dev <= tol).all()
     assert abs(diss - float(g["dissipation"])) <= max(TOL * abs(float(g["dissipation"])), 4 * float(g["dissipation_sem"]))
@@ -107,5 +128,5 @@ def test_spectral_solver_statistics_vs_its_oracle():
     assert abs(rew - float(g["mean_reward"])) <= max(TOL * abs(float(g["mean_reward"])), 4 * float(g["mean_reward_sem"]))
     # and the recorded distance between the two discretisations is what the fixture says it is:
     # a few per cent in the low wavenumbers, i.e. NOT within the 1 % gate of the reference scheme
-    fd = np.load(os.path.join(GOLDEN, "stats_default.npz"))
-    assert abs(u2 / float(fd["mean_u2"]) - 1) < 0.03
+    fd = np.load(os.path.join(GOLDEN, "stats_" + name.split("_", 1)[1] + ".npz"))
+    assert abs(u2 / float(fd["mean_u2"]) - 1) < 0.05

@@ -27,8 +27,39 @@ def parse(path, name):
     raise SystemExit(f"kernel {name!r} not found")
 
 
+def table(path, out_path):
+    """FP64 / total instruction counts of the sub-step loop of every ks_period_kernel<double, P, 0> in `path`
+    -> JSON {"P": {"fp64": n, "issue": n, "dfma": n, ...}} (bench.py: roofline.frac_executed)."""
+    import io
+    import json
+    from contextlib import redirect_stdout
+
+    res = {"_comment": "instructions per warp per RK4 sub-step in the inner loop of ks_period_kernel<double,P,0>, "
+                       "from cuobjdump -sass of the shipped objects (tools/sass_stats.py --table); one FP64 "
+                       "instruction = one FP64-pipe slot = 2 flop-equivalents per lane"}
+    for P in range(4, 17):
+        buf = io.StringIO()
+        try:
+            with redirect_stdout(buf):
+                analyse(path, f"ks_period_kernelIdLi{P}ELi0E")
+        except SystemExit:
+            continue
+        txt = buf.getvalue()
+        mix = eval(re.search(r"mix: (\{.*\})", txt).group(1))
+        res[str(P)] = {"fp64": sum(v for k, v in mix.items() if k in FP64), "issue": sum(mix.values()),
+                       "mix": mix, "rf_cycles": float(re.search(r"RF cycles (\d+)", txt).group(1))}
+    with open(out_path, "w") as f:
+        json.dump(res, f, indent=1)
+    print("wrote", out_path)
+
+
 def main():
-    path, name = sys.argv[1], sys.argv[2]
+    if sys.argv[1] == "--table":
+        return table(sys.argv[2], sys.argv[3])
+    analyse(sys.argv[1], sys.argv[2])
+
+
+def analyse(path, name):
     head, body = parse(path, name)
     ins = []
     for ln in body.split("\n"):
