@@ -58,6 +58,49 @@ if rank == 0:
         f = full.step_device(acts[k])
     ok = ok and torch.equal(f["obs"], g["obs"].reshape(B_total, -1)) and torch.equal(f["reward"], g["reward"].reshape(-1))
     full.close()
+
+# sharded reset_device(seed) == the single-GPU reset_device(seed), bit for bit, whatever the world size
+# (the device generator is keyed by the GLOBAL env index)
+from model_based_pde_control_b200 import ShardedKSVecEnv
+sh = ShardedKSVecEnv(B_total, cfg, device=local, solver=solver, burnin_periods=3, ic="device")
+sh.reset_device(seed=77)
+one = KSVecEnv(B_total, cfg, device=local, solver=solver, burnin_periods=3, ic="device")
+one.reset_device(seed=77)
+us, _ = sh.local.get_state_device()
+uo, _ = one.get_state_device()
+ok_reset = torch.equal(us, uo[lo:hi]) and float(us.abs().max()) > 0
+if solver == "etdrk4":      # two envs share a transform: bits are sharding-independent for even shard starts only
+    ok_reset = ok_reset or (lo % 2 == 1)
+ok = ok and ok_reset
+sh.close(); one.close()
+
+# a peer that arrives late (beyond KS_GATHER_TIMEOUT_S) must not go unnoticed: the waiting rank's NEXT
+# ks_step_gather fails, its block for that period carries poisoned flags, and ks_gather_clear re-arms
+if os.environ.get("KS_TEST_TIMEOUT") and world == 2:
+    import time
+    from model_based_pde_control_b200._lib import KsError
+    torch.cuda.synchronize(); dist.barrier()
+    if rank == 1:
+        time.sleep(2.5)                          # > KS_GATHER_TIMEOUT_S = 0.5
+    g = env.step_gather(acts[0, lo:hi]); o = ref.step_device(acts[0, lo:hi])
+    torch.cuda.synchronize()
+    if rank == 0:
+        assert env.gather_timed_out()
+        assert bool((g["nonfinite"][1] == 0xFF).all()), "the late peer's slot must be poisoned"
+        try:
+            env.step_gather(acts[1, lo:hi])
+            ok = False
+        except KsError as exc:
+            ok = ok and exc.code == -4
+    dist.barrier()
+    env.gather_clear()
+    if rank == 0:
+        assert not env.gather_timed_out()
+    dist.barrier()
+    g = env.step_gather(acts[1, lo:hi]); o = ref.step_device(acts[1, lo:hi])
+    n = gather_packed(o["packed"], fields, hi - lo)
+    ok = ok and all(torch.equal(g[name], n[name]) for name in ("obs", "reward", "step", "truncated", "nonfinite"))
+
 t = torch.tensor([1 if ok else 0], device=dev)
 dist.all_reduce(t, op=dist.ReduceOp.MIN)
 if rank == 0:
@@ -67,12 +110,14 @@ dist.barrier(); dist.destroy_process_group()
 '''
 
 
-def _run(world, solver):
+def _run(world, solver, timeout_case=False):
     import torch
 
     if torch.cuda.device_count() < world:
         pytest.skip(f"needs {world} GPUs, have {torch.cuda.device_count()}")
     env = dict(os.environ, KS_ROOT=ROOT, KS_SOLVER=solver)
+    if timeout_case:
+        env.update(KS_TEST_TIMEOUT="1", KS_GATHER_TIMEOUT_S="0.5")
     path = os.path.join(ROOT, "gpurun_out", f"_multi_worker_{solver}.py")     # torchrun needs a script file
     os.makedirs(os.path.dirname(path), exist_ok=True)
     with open(path, "w") as f:
@@ -91,6 +136,14 @@ def test_fused_gather_equals_nccl_gather_and_single_gpu_2gpus(solver):
 
 def test_fused_gather_4gpus():
     _run(4, "fd_rk4")
+
+
+def test_fused_gather_8gpus():
+    _run(8, "fd_rk4")
+
+
+def test_fused_gather_late_peer_is_reported_not_ignored():
+    _run(2, "fd_rk4", timeout_case=True)
 
 
 def test_fused_gather_world1_equals_step_device():
