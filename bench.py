@@ -306,8 +306,9 @@ def fd_roofline(env, B, kernel_ms, precision, peaks):
     out["traffic"] = (t["dram_bytes_read"] + t["dram_bytes_write"]) if t else None
     out["traffic_unit"] = "bytes per launch (dram read+write, ncu --set full capture of this configuration; static, see source)"
     out["traffic_source"] = t["source"] if t else None
-    if t and "fp64_pipe_pct" in t:
-        out["ncu_fp64_pipe_pct"] = t["fp64_pipe_pct"]
+    if t and "pipe_active_pct" in t:      # what ncu measured for the same configuration (compare with frac_executed)
+        out["ncu_pipe_active_pct"] = {"pipe": t["pipe"], "pct": t["pipe_active_pct"], "issue_active_pct": t.get("issue_active_pct"),
+                                      "source": t["source"]}
     return out
 
 
@@ -444,6 +445,8 @@ def run_gpu_arm(args):
         for this rank's slot.  All ranks agree on the verdict; a mismatch aborts the run."""
         if not state["fused"]:
             return None
+        if os.environ.get("KS_GATHER_DEBUG"):      # measurement knobs that break the completion guarantee
+            return "skipped (KS_GATHER_DEBUG=%s: cost-breakdown run, results not guaranteed complete)" % os.environ["KS_GATHER_DEBUG"]
         twin = make_env(env.num_envs, precision=precision, points_per_lane=ppl)
         rng = np.random.default_rng(4242 + rank)
         u0 = rng.uniform(-1.0, 1.0, (env.num_envs, env.N))

@@ -187,6 +187,20 @@ int choose_points_per_lane(int N, long long B, int sm_count)
     return best;
 }
 
+// Registers per lane of the spectral kernel at N = 64: 8 (ks_etd.cuh: 8 lanes x 8 complex registers per
+// env pair, 8 envs per warp) or 4 (ks_etd16.cuh: 16 lanes x 4, 4 envs per warp).  Measured on B200
+// (profiles/round2_sweep_etd_layouts.jsonl): a warp alone on its SM sub-partition needs 23.3 us per control
+// period (10 ETDRK4 steps) in the 16-lane layout and 29.3 us in the 8-lane layout -- its dependent chain
+// is half as long -- so the 16-lane layout is 20 % faster as long as every warp has a sub-partition to
+// itself (B <= 4 x 592 = 2368 envs).  Beyond that it loses: it moves every value through the
+// shared-memory crossbar twice per transform instead of once (600 against 688 wavefronts per warp-step for
+// half the envs), and the crossbar (128 B/clk/SM) is what bounds this solver at large batches.
+int choose_etd_regs_per_lane(long long B, int sm_count)
+{
+    const long long smsp = 4LL * (sm_count > 0 ? sm_count : 148);
+    return (B + 3) / 4 <= smsp ? 4 : 8;
+}
+
 // ---------------------------------------------------------------------------------------------
 // auxiliary kernels
 // ---------------------------------------------------------------------------------------------
@@ -409,12 +423,28 @@ __global__ void collect_apply(const ks_collect_args a, int B, int No, int J, con
 
 __global__ void collect_advance(int64_t *slot_index) { *slot_index += 1; }
 
+// KS_GATHER_DEBUG (measurement only, profiles/README.md "exchange cost breakdown"): "nofence" leaves out the
+// system-scope fence at the end of the period kernel, "nosignal" the signal / wait kernel.  Results are then
+// NOT guaranteed to be complete when the stream reaches the consumer; bench.py refuses to verify such a run.
+int gather_debug()
+{
+    static const int flags = []() {
+        const char *e = getenv("KS_GATHER_DEBUG");
+        int f = 0;
+        if (e && strstr(e, "nofence")) f |= 1;
+        if (e && strstr(e, "nosignal")) f |= 2;
+        return f;
+    }();
+    return flags;
+}
+
 int launch_period(ks_handle *h, int K, const float *actions, const float *phi, float *obs, double *reward,
                   uint8_t *truncated, int32_t *step, uint8_t *nonfinite_out, int reset_timestep, const uint8_t *mask,
                   cudaStream_t stream, int n_remote = 0, const long long *remote_delta = nullptr)
 {
     ks::Params p;
     p.n_remote = n_remote;
+    p.skip_fence = (n_remote > 0 && (gather_debug() & 1)) ? 1 : 0;
     for (int q = 0; q < ks::kMaxRemote; ++q) p.remote_delta[q] = q < n_remote ? remote_delta[q] : 0;
     p.u = h->u;
     p.timestep = h->timestep;
@@ -489,12 +519,16 @@ int ks_create(const ks_config *cfg, ks_handle **out)
     if (etd && cfg->N != 64 && cfg->N != 128 && cfg->N != 256)
         return fail(nullptr, KS_ERR_UNSUPPORTED, "ks_create: the spectral ETDRK4 solver supports N = 64, 128, 256 (N=%d)", cfg->N);
 
-    int P = etd ? 8 : cfg->points_per_lane;
-    if (P != 0 && (P < ks::kMinP || P > ks::kMaxP || cfg->N % P || cfg->N / P > 32))
+    // spectral solver: points_per_lane = complex registers per lane, 8 (all N) or 4 (N = 64 only), 0 = automatic
+    if (etd && cfg->points_per_lane != 0 && cfg->points_per_lane != 8 && !(cfg->points_per_lane == 4 && cfg->N == 64))
+        return fail(nullptr, KS_ERR_UNSUPPORTED,
+                    "ks_create: the spectral solver takes points_per_lane = 0, 8, or (N = 64 only) 4 (got %d)", cfg->points_per_lane);
+    int P = etd ? (cfg->N == 64 ? cfg->points_per_lane : 8) : cfg->points_per_lane;
+    if (!etd && P != 0 && (P < ks::kMinP || P > ks::kMaxP || cfg->N % P || cfg->N / P > 32))
         return fail(nullptr, KS_ERR_UNSUPPORTED,
                     "ks_create: N=%d needs N = lanes*P with 4<=P<=16, lanes<=32 (points_per_lane=%d)", cfg->N,
                     cfg->points_per_lane);
-    if (P == 0 && choose_points_per_lane(cfg->N, cfg->num_envs, 0) == 0)
+    if (!etd && P == 0 && choose_points_per_lane(cfg->N, cfg->num_envs, 0) == 0)
         return fail(nullptr, KS_ERR_UNSUPPORTED, "ks_create: N=%d cannot be split as lanes*P with 4<=P<=16, lanes<=32",
                     cfg->N);
 
@@ -510,7 +544,9 @@ int ks_create(const ks_config *cfg, ks_handle **out)
     if (cudaGetDeviceProperties(&prop, cfg->device) != cudaSuccess || prop.major != 10)
         return fail(nullptr, KS_ERR_NO_DEVICE, "ks_create: device %d is sm_%d%d; kernels are built for sm_100a only",
                     cfg->device, prop.major, prop.minor);
-    if (P == 0) P = choose_points_per_lane(cfg->N, cfg->num_envs, prop.multiProcessorCount);
+    if (P == 0)
+        P = etd ? choose_etd_regs_per_lane(cfg->num_envs, prop.multiProcessorCount)
+                : choose_points_per_lane(cfg->N, cfg->num_envs, prop.multiProcessorCount);
 
     ks_handle *h = new (std::nothrow) ks_handle();
     if (!h) return fail(nullptr, KS_ERR_ARG, "ks_create: out of host memory");
@@ -536,6 +572,13 @@ int ks_create(const ks_config *cfg, ks_handle **out)
         const int per_cta = h->envs_per_warp * (ks::kBlockThreads / 32);
         h->grid = (int)((cfg->num_envs + per_cta - 1) / per_cta);
         h->kernel = f64 ? ks::etd_kernel_f64(R, cfg->reward_mode) : ks::etd_kernel_f32(R, cfg->reward_mode);
+        if (P == 4) {      // small-batch layout: 16 lanes x 4 registers per pair, 4 envs per warp (ks_etd16.cuh)
+            h->lanes = 16;
+            h->envs_per_warp = 4;
+            const int per_cta16 = 4 * (ks::kBlockThreads / 32);
+            h->grid = (int)((cfg->num_envs + per_cta16 - 1) / per_cta16);
+            h->kernel = f64 ? ks::etd16_kernel_f64(cfg->reward_mode) : ks::etd16_kernel_f32(cfg->reward_mode);
+        }
     }
     const double dx = cfg->L / cfg->N;  // kuramoto.py:55
     fill_coef(h->c64, dx, cfg->dt);
@@ -931,7 +974,7 @@ int ks_step_gather(ks_handle *h, const float *actions, void **gathered, void *st
                            mine + h->out_off[3], (int32_t *)(mine + h->out_off[2]), mine + h->out_off[4], 0, nullptr, stream,
                            n, delta);
     if (rc != KS_OK) return rc;
-    if (h->g_world > 1) {
+    if (h->g_world > 1 && !(gather_debug() & 2)) {
         gather_signal_wait<<<1, 32, 0, stream>>>(reinterpret_cast<uint32_t *const *>(h->g_timeout + 2),
                                                  reinterpret_cast<volatile uint32_t *>(h->g_buf + h->g_flags_off), h->g_world,
                                                  h->g_rank, h->g_epoch, h->g_timeout_host, h->g_timeout_cycles,

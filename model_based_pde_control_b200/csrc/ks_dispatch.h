@@ -16,6 +16,9 @@ const void *period_kernel_f32_diss(int P);
 // Spectral ETDRK4 solver (ks_etd.cuh, N = 64 R): one kernel per precision, R in {1, 2, 4} and reward mode.
 const void *etd_kernel_f64(int R, int reward_mode);
 const void *etd_kernel_f32(int R, int reward_mode);
+// Small-batch layout of the same solver (ks_etd16.cuh, N = 64: 16 lanes x 4 registers per env pair).
+const void *etd16_kernel_f64(int reward_mode);
+const void *etd16_kernel_f32(int reward_mode);
 
 }  // namespace ks
 

@@ -615,7 +615,7 @@ __global__ void __launch_bounds__(kBlockThreads, KS_ETD_MIN_BLOCKS) ks_etd_kerne
             }
         }
     }
-    if (p.n_remote > 0) __threadfence_system();   // peer stores performed before the launch retires
+    if (p.n_remote > 0 && !p.skip_fence) __threadfence_system();   // peer stores performed before the launch retires
 
 #pragma unroll
     for (int r = 0; r < 8; ++r) {

@@ -4,11 +4,14 @@
 // differs is how a pair of envs is spread over the warp.  ks_etd.cuh gives a pair 8 lanes x 8
 // complex registers: 8 envs per warp, 255 registers, so a batch of 4096 envs is 512 warps -- one
 // warp on 512 of the B200's 592 SM sub-partitions, nothing to overlap its dependent FFT stages
-// with (FP64 pipe 52 % busy, 0.32 of the roofline).  Here a pair occupies 16 lanes x 4 complex
-// registers: 4 envs per warp, about half the registers, twice the warps, and every warp's
-// dependent chain is half as long.  ks_create picks this layout for batches that cannot give the
-// 8-lane layout two warps per sub-partition (ks_api.cu, choose_etd_regs_per_lane); at large
-// batches the 8-lane layout wins (8 % fewer FP64 instructions per env, half the exchange traffic).
+// with.  Here a pair occupies 16 lanes x 4 complex registers: 4 envs per warp, 168 registers, twice
+// the warps, and every warp's dependent chain is half as long: 23.3 us instead of 29.3 us per
+// control period for a warp that has its sub-partition to itself.  ks_create therefore picks this
+// layout for batches of up to 4 x 592 = 2368 envs (ks_api.cu, choose_etd_regs_per_lane).  Beyond
+// that the 8-lane layout wins (measured, profiles/round2_sweep_etd_layouts.jsonl: 4096 envs 29.3
+// against 34.9 us, 65 536 envs 0.271 against 0.382 ms): this layout needs two exchanges per transform
+// instead of one, i.e. twice the shared-memory crossbar traffic per env, and the crossbar
+// (128 B/clk/SM) is the co-bottleneck of the spectral solver.
 //
 // 64-point FFT on 16 lanes x 4 registers: three radix-4 stages in registers with two 4x4
 // exchanges between them.  With n = n0 + 4 n1 + 16 n2 and k = k2 + 4 k1 + 16 k0,
@@ -29,6 +32,10 @@
 #include "ks_etd.cuh"
 
 namespace ks {
+
+#ifndef KS_ETD16_MIN_BLOCKS
+#define KS_ETD16_MIN_BLOCKS 3
+#endif
 
 // 4-point DFT in registers, forward sign (W4 = -i), natural order in and out: 16 additions.
 template <typename T>
@@ -192,7 +199,7 @@ __device__ __forceinline__ void nonlinear16(T (&wx)[4], T (&wy)[4], const Fft16C
 // The spectral control-period kernel, 16 lanes x 4 registers per env pair: 4 envs per warp.
 // ---------------------------------------------------------------------------------------------
 template <typename T, int RMODE>
-__global__ void __launch_bounds__(kBlockThreads, 3) ks_etd16_kernel(const EtdParams ep)
+__global__ void __launch_bounds__(kBlockThreads, KS_ETD16_MIN_BLOCKS) ks_etd16_kernel(const EtdParams ep)
 {
     const Params &p = ep.p;
     constexpr int N = kEtdN;
@@ -477,7 +484,7 @@ __global__ void __launch_bounds__(kBlockThreads, 3) ks_etd16_kernel(const EtdPar
             }
         }
     }
-    if (p.n_remote > 0) __threadfence_system();   // peer stores performed before the launch retires
+    if (p.n_remote > 0 && !p.skip_fence) __threadfence_system();   // peer stores performed before the launch retires
 
 #pragma unroll
     for (int r = 0; r < 4; ++r) {

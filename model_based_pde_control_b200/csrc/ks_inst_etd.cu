@@ -2,6 +2,7 @@
 // N = 64 R with R = 1, 2, 4, both reward modes.
 #include "ks_dispatch.h"
 #include "ks_etd.cuh"
+#include "ks_etd16.cuh"
 
 #define KS_ETD_LOOKUP(NAME, T)                                                                        \
     const void *ks::NAME(int R, int rmode)                                                            \
@@ -19,3 +20,15 @@
     }
 KS_ETD_LOOKUP(etd_kernel_f64, double)
 KS_ETD_LOOKUP(etd_kernel_f32, float)
+
+// Small-batch layout (ks_etd16.cuh): N = 64, 16 lanes x 4 registers per env pair.
+const void *ks::etd16_kernel_f64(int rmode)
+{
+    return rmode == ks::kRewardL2 ? (const void *)&ks::ks_etd16_kernel<double, ks::kRewardL2>
+                                  : (const void *)&ks::ks_etd16_kernel<double, ks::kRewardDissipation>;
+}
+const void *ks::etd16_kernel_f32(int rmode)
+{
+    return rmode == ks::kRewardL2 ? (const void *)&ks::ks_etd16_kernel<float, ks::kRewardL2>
+                                  : (const void *)&ks::ks_etd16_kernel<float, ks::kRewardDissipation>;
+}

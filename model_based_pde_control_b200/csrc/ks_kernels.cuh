@@ -62,6 +62,7 @@ struct Params {
     // `pointer + remote_delta[q]`, q < n_remote -- this rank's slot in peer q's gather buffer, mapped
     // into this process with CUDA IPC, i.e. plain st.global over NVLink.  n_remote = 0 otherwise.
     int n_remote;
+    int skip_fence;        // measurement knob (KS_GATHER_DEBUG=nofence): leave out the system-scope fence at kernel end
     long long remote_delta[kMaxRemote];
 };
 
@@ -461,7 +462,7 @@ __global__ void __launch_bounds__(kBlockThreads) ks_period_kernel(const Params p
             __syncwarp();
         }
     }
-    if (p.n_remote > 0) __threadfence_system();   // peer stores performed before the launch retires
+    if (p.n_remote > 0 && !p.skip_fence) __threadfence_system();   // peer stores performed before the launch retires
 
     if (active) {
         store_row<P>(ug, u);

@@ -29,14 +29,16 @@ dev = torch.device("cuda", local)
 dist.init_process_group("nccl", device_id=dev)
 solver = os.environ.get("KS_SOLVER", "fd_rk4")
 cfg = dict(dt=0.025, cfg_steps=10) if solver == "etdrk4" else dict(cfg_steps=25)
-B_total, K = 1020, 12      # 510 envs per rank at world 2: the last thread block has an early-exit warp
+B_total, K = (1020 if 1020 % world == 0 else 127 * world), 12      # equal shards (the fused exchange requires them);
+                                                                   # 510 envs per rank at world 2: the last thread block has an early-exit warp
 lo, hi = shard_range(B_total, rank, world)
 rng = np.random.default_rng(0)
 u0 = rng.uniform(-1, 1, (B_total, 64))
 acts = torch.as_tensor(rng.uniform(-1, 1, (K, B_total, 4)).astype(np.float32)).to(dev)
 
-env = KSVecEnv(hi - lo, cfg, device=local, solver=solver)          # fused path
-ref = KSVecEnv(hi - lo, cfg, device=local, solver=solver)          # NCCL path
+ppl = int(os.environ.get("KS_PPL", "0"))                           # spectral solver: 8 = 8-lane layout, 0 = automatic (16-lane here)
+env = KSVecEnv(hi - lo, cfg, device=local, solver=solver, points_per_lane=ppl)          # fused path
+ref = KSVecEnv(hi - lo, cfg, device=local, solver=solver, points_per_lane=ppl)          # NCCL path
 env.set_state(u0[lo:hi], 0); ref.set_state(u0[lo:hi], 0)
 connect_fused_gather(env)
 fields = ref.packed_fields()
@@ -52,7 +54,7 @@ assert not env.gather_timed_out()
 
 # the gathered batch equals the single-GPU run of all envs (rank 0 computes it)
 if rank == 0:
-    full = KSVecEnv(B_total, cfg, device=local, solver=solver)
+    full = KSVecEnv(B_total, cfg, device=local, solver=solver, points_per_lane=ppl)
     full.set_state(u0, 0)
     for k in range(K):
         f = full.step_device(acts[k])
@@ -110,12 +112,12 @@ dist.barrier(); dist.destroy_process_group()
 '''
 
 
-def _run(world, solver, timeout_case=False):
+def _run(world, solver, timeout_case=False, ppl=0):
     import torch
 
     if torch.cuda.device_count() < world:
         pytest.skip(f"needs {world} GPUs, have {torch.cuda.device_count()}")
-    env = dict(os.environ, KS_ROOT=ROOT, KS_SOLVER=solver)
+    env = dict(os.environ, KS_ROOT=ROOT, KS_SOLVER=solver, KS_PPL=str(ppl))
     if timeout_case:
         env.update(KS_TEST_TIMEOUT="1", KS_GATHER_TIMEOUT_S="0.5")
     path = os.path.join(ROOT, "gpurun_out", f"_multi_worker_{solver}.py")     # torchrun needs a script file
@@ -125,13 +127,14 @@ def _run(world, solver, timeout_case=False):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
            "--master-addr", "127.0.0.1", "--master-port", "29611", path]
     res = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=300)
-    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-4000:]
+    errs = "\n".join(ln for ln in res.stderr.splitlines() if "Error" in ln or "error" in ln or "assert" in ln)[:3000]
+    assert res.returncode == 0, res.stdout[-2000:] + errs + res.stderr[-3000:]
     assert "MULTI_GPU_OK" in res.stdout, res.stdout[-2000:] + res.stderr[-2000:]
 
 
-@pytest.mark.parametrize("solver", ["fd_rk4", "etdrk4"])
-def test_fused_gather_equals_nccl_gather_and_single_gpu_2gpus(solver):
-    _run(2, solver)
+@pytest.mark.parametrize("solver,ppl", [("fd_rk4", 0), ("etdrk4", 0), ("etdrk4", 8)])
+def test_fused_gather_equals_nccl_gather_and_single_gpu_2gpus(solver, ppl):
+    _run(2, solver, ppl=ppl)
 
 
 def test_fused_gather_4gpus():

@@ -19,12 +19,33 @@ TOL32 = 1e-4
 DT, S = 0.025, 10          # 10 ETDRK4 steps of 0.025 = the reference's 0.25 time units per control period
 
 
+# Two lane layouts of the same solver at N = 64: 8 lanes x 8 registers per env pair (csrc/ks_etd.cuh, large
+# batches) and 16 lanes x 4 registers (csrc/ks_etd16.cuh, small batches; what ks_create picks by itself
+# for every batch size used here).  Every test of this file runs with both.
+_PPL = {"value": 0}
+
+
+@pytest.fixture(autouse=True, params=[4, 8], ids=["16lanes", "8lanes"])
+def etd_layout(request):
+    _PPL["value"] = request.param
+    yield request.param
+    _PPL["value"] = 0
+
+
+def ppl(N=64):
+    return _PPL["value"] if N == 64 else 0
+
+
 def make_env(B, **kw):
     from model_based_pde_control_b200 import KSVecEnv
 
     kw.setdefault("dt", DT)
     kw.setdefault("cfg_steps", S)
-    return KSVecEnv(B, solver="etdrk4", **kw)
+    kw.setdefault("points_per_lane", ppl(kw.get("N", 64)))
+    env = KSVecEnv(B, solver="etdrk4", **kw)
+    if env.N == 64:
+        assert env.launch_info()["lanes_per_env"] == (16 if _PPL["value"] == 4 else 8)
+    return env
 
 
 def oracle_step(env, u0, actions, **kw):
@@ -108,7 +129,7 @@ def test_dissipation_reward_mode(N, L, J, B):
 
     rng = np.random.default_rng(N)
     env = KSVecEnv(B, dict(N=N, L=L, dt=DT, cfg_steps=S), Xi=[k / J for k in range(J)], solver="etdrk4",
-                   reward_mode="dissipation")
+                   reward_mode="dissipation", points_per_lane=ppl(N))
     u0 = np.concatenate([smooth_states(rng, B, 64)] * (N // 64), axis=1) * 0.7 + rng.uniform(-0.1, 0.1, (B, N))
     a = rng.uniform(-1, 1, (B, 1, J)).astype(np.float32)
     env.set_state(u0, 0)
@@ -119,7 +140,8 @@ def test_dissipation_reward_mode(N, L, J, B):
     assert rel_l2(u1, u_ref).max() <= TOL64
     assert np.abs((rew - r_ref) / r_ref).max() <= TOL64, np.abs((rew - r_ref) / r_ref).max()
     # the state does not depend on the reward mode (two kernel instantiations: equal up to rounding)
-    env2 = KSVecEnv(B, dict(N=N, L=L, dt=DT, cfg_steps=S), Xi=[k / J for k in range(J)], solver="etdrk4")
+    env2 = KSVecEnv(B, dict(N=N, L=L, dt=DT, cfg_steps=S), Xi=[k / J for k in range(J)], solver="etdrk4",
+                    points_per_lane=ppl(N))
     env2.set_state(u0, 0)
     _, rew_l2, *_ = env2.step(a)
     assert rel_l2(env2.get_state()[0], u1).max() < 1e-13 and not np.allclose(rew_l2, rew)
