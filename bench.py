@@ -168,8 +168,11 @@ def shared_config(B, world, N, L, J, S, dt, precision, gather):
         "l2": "GPU arm: L2 flushed (256 MiB memset) between timed steps, outside the per-step CUDA-event pairs; at N>1 the "
               "ranks are re-aligned after each flush by a 4-byte all-reduce, also outside the pairs.  CPU arm: not applicable",
         "collective": "GPU arm at N>1 (--gather %s): %s; N=1 and CPU arm: none" % (gather, {
-            "fused": "the period kernel's epilogue stores the packed obs/reward/step/truncated/flags block into every peer's "
-                     "gather buffer over NVLink (CUDA-IPC peer stores) + one-warp epoch handshake, inside the timed region",
+            "fused": "the period kernel's epilogue stores the packed obs/reward/step/truncated/flags block into every rank's "
+                     "gather buffer over NVLink + one-warp epoch handshake, inside the timed region; `gather_mode` says which "
+                     "transport ran: fused_mc (symmetric memory, observation rows sent once through an NVLS multicast address, "
+                     "multimem.st) or fused_ipc (CUDA-IPC mapped peer buffers, one store per peer)",
+            "fused_mc": "forced fused_mc (see fused)", "fused_ipc": "forced fused_ipc (see fused)",
             "nccl": "one NCCL all-gather of the packed obs/reward/step/truncated/flags block per period, inside the timed region",
             "none": "NONE (diagnostic run: every rank keeps its shard to itself)"}[gather]),
     }
@@ -366,7 +369,7 @@ def run_gpu_arm(args):
     import torch.distributed as dist
 
     from model_based_pde_control_b200 import KSVecEnv, _lib
-    from model_based_pde_control_b200.sharding import connect_fused_gather, gather_packed
+    from model_based_pde_control_b200.sharding import connect_fused_gather, connect_fused_gather_symm, gather_packed
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -393,7 +396,7 @@ def run_gpu_arm(args):
     stream = torch.cuda.current_stream(dev)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
     align = torch.zeros(1, device=dev)
-    state = {"fused": world > 1 and args.gather == "fused", "gather": args.gather, "note": None}
+    notes = []
 
     def allmax(x: float) -> float:
         if world == 1:
@@ -414,37 +417,13 @@ def run_gpu_arm(args):
         env.set_state(None, 0)
         return torch.as_tensor(rng.uniform(-1, 1, (Ksteps, env.num_envs, env.J)).astype(np.float32)).to(dev)
 
-    def connect(env):
-        """CUDA-IPC handles exchanged once; afterwards no collective call per period.  If peer mapping is
-        not possible on this box (ranks in different IPC namespaces, no P2P), every rank switches to the
-        NCCL all-gather together and the JSON line says so -- the exchange is never skipped."""
-        if not state["fused"]:
-            return
-        try:
-            connect_fused_gather(env)         # raises on every rank if any rank fails
-        except Exception as exc:              # noqa: BLE001 - reported in the JSON line
-            state["fused"], state["gather"] = False, "nccl"
-            state["note"] = f"fused exchange unavailable ({type(exc).__name__}: {exc}); NCCL all-gather used"
-            print(state["note"], file=sys.stderr)
-
-    def stepper(env):
-        fields, n = env.packed_fields(), env.num_envs
-
-        def one_step(a):
-            if state["fused"]:
-                return env.step_gather(a)     # kernel epilogue stores into every peer's buffer + handshake
-            out = env.step_device(a)
-            if world > 1 and state["gather"] == "nccl":
-                out = gather_packed(out["packed"], fields, n)
-            return out
-        return one_step
+    def fused(env):
+        return getattr(env, "_bench_mode", "none") in ("fused_mc", "fused_ipc")
 
     def verify_gather(env, precision, ppl):
         """The fused exchange against two independent routes, bit for bit, both buffer parities:
         (i) an NCCL all-gather of a twin shard's packed block, (ii) the twin's own (single-GPU) outputs
-        for this rank's slot.  All ranks agree on the verdict; a mismatch aborts the run."""
-        if not state["fused"]:
-            return None
+        for this rank's slot.  All ranks agree on the verdict."""
         if os.environ.get("KS_GATHER_DEBUG"):      # measurement knobs that break the completion guarantee
             return "skipped (KS_GATHER_DEBUG=%s: cost-breakdown run, results not guaranteed complete)" % os.environ["KS_GATHER_DEBUG"]
         twin = make_env(env.num_envs, precision=precision, points_per_lane=ppl)
@@ -464,9 +443,56 @@ def run_gpu_arm(args):
         twin.close()
         t = torch.tensor([1.0 if ok else 0.0], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MIN)
-        if float(t.item()) != 1.0:
-            raise SystemExit("gather_verified: the fused exchange differs from the NCCL all-gather / single-GPU run")
-        return True
+        return float(t.item()) == 1.0
+
+    def connected_env(n, precision, ppl):
+        """A local shard of n envs with the per-period exchange set up, and whether it was verified.
+        --gather fused (default) tries, in this order, and every rank takes the same branch:
+          fused_mc   torch symmetric-memory buffers + NVLS multicast address: the period kernel sends its observation
+                     rows once (multimem.st), the NVSwitch replicates them; small outputs + handshake unicast
+          fused_ipc  CUDA-IPC mapped peer buffers, every store once per peer (round 1's path)
+          nccl       one NCCL all-gather of the packed block per period
+        A mode is used only if its set-up succeeded on EVERY rank and its results were verified bit for bit; the
+        JSON line names the mode that ran (`gather_mode`) and why earlier ones were passed over (`collective_note`)."""
+        order = {"fused": ["fused_mc", "fused_ipc", "nccl"], "fused_mc": ["fused_mc"], "fused_ipc": ["fused_ipc"],
+                 "nccl": ["nccl"], "none": ["none"]}[args.gather if world > 1 else "none"]
+        for i, mode in enumerate(order):
+            env = make_env(n, precision=precision, points_per_lane=ppl)
+            env._bench_mode = mode
+            if mode in ("nccl", "none"):
+                return env, None
+            try:
+                if mode == "fused_mc":
+                    if args.solver != "fd_rk4":
+                        raise RuntimeError("multicast stores are built into the FD-RK4 kernel only")
+                    info = connect_fused_gather_symm(env)         # raises on every rank if any rank fails
+                    if not info["multicast"]:
+                        raise RuntimeError("symmetric memory gave no multicast address on some rank")
+                else:
+                    connect_fused_gather(env)
+                verdict = verify_gather(env, precision, ppl)
+                if verdict is not False:
+                    return env, verdict
+                why = "results differ from the NCCL all-gather / single-GPU run"
+            except Exception as exc:              # noqa: BLE001 - reported in the JSON line
+                why = f"{type(exc).__name__}: {exc}"
+            env.close()
+            if i + 1 == len(order):
+                raise SystemExit(f"--gather {args.gather}: {mode} failed ({why})")
+            notes.append(f"{mode} passed over ({why})")
+            print(notes[-1], file=sys.stderr)
+
+    def stepper(env):
+        fields, n, mode = env.packed_fields(), env.num_envs, getattr(env, "_bench_mode", "none")
+
+        def one_step(a):
+            if mode in ("fused_mc", "fused_ipc"):
+                return env.step_gather(a)     # kernel epilogue stores into every peer's buffer + handshake
+            out = env.step_device(a)
+            if mode == "nccl":
+                out = gather_packed(out["packed"], fields, n)
+            return out
+        return one_step
 
     def timed(env, actions, Ksteps, Wsteps):
         """W warm-up + K timed steps: one CUDA-event pair per step on the launching stream, L2 flush
@@ -505,16 +531,14 @@ def run_gpu_arm(args):
 
     def check_health(env):
         bad = bool(env.nonfinite().any())
-        if state["fused"] and env.gather_timed_out():
+        if fused(env) and env.gather_timed_out():
             raise SystemExit("fused gather: a peer never signalled (handshake timed out)")
         return bad
 
     # =========================================== headline: 4096 envs per GPU =======================
-    env = make_env(B, precision=args.precision, points_per_lane=args.points_per_lane)
+    env, gather_verified = connected_env(B, args.precision, args.points_per_lane)
     N, J, S = env.N, env.J, env.cfg_steps
     total_envs = B * world
-    connect(env)
-    gather_verified = verify_gather(env, args.precision, args.points_per_lane)
     actions = prepare(env, 1000, W + K)
 
     sampler = ClockSampler(local_rank)
@@ -603,9 +627,7 @@ def run_gpu_arm(args):
     if not args.no_config_65536 and not spectral and args.precision == "f64":
         B2 = TOTAL_ENVS_CONFIG2 // world
         K2 = min(K, 20)
-        env2 = make_env(B2)
-        connect(env2)
-        v2 = verify_gather(env2, "f64", 0)
+        env2, v2 = connected_env(B2, "f64", 0)
         a2 = prepare(env2, 3000, W + K2)
         ms2, l2, _ = timed(env2, a2, K2, W)
         bad2 = check_health(env2)
@@ -654,11 +676,11 @@ def run_gpu_arm(args):
         "nonfinite": flags_bad,
         "value_kind": "burst (K short steps); see `sustained` for >= 2 s of the same step",
     }
-    if state["note"]:
-        line["collective_note"] = state["note"]
+    if notes:
+        line["collective_note"] = "; ".join(notes)
     if world > 1:
         line["gather_verified"] = gather_verified
-        line["gather_mode"] = "fused" if state["fused"] else state["gather"]
+        line["gather_mode"] = env._bench_mode
     if sustained:
         if not spectral:
             sustained["roofline"] = {k: v for k, v in fd_roofline(env, B, sustained["ms_per_step"], args.precision, peaks).items()
@@ -674,7 +696,7 @@ def run_gpu_arm(args):
             "scaling": "strong", "n_gpus": world, "gpu_launches": int(config2["launches"]), "nonfinite": config2["bad"],
             "config": {"workload": f"BASELINE.json configs[2]: {TOTAL_ENVS_CONFIG2} KS envs over {world} GPU(s) = {B2} per GPU, N={N} "
                                    f"L={env.L} J={J}, cfg_steps={S}, dt={env.dt}, f64, random actions; exchange "
-                                   f"{'fused peer stores' if state['fused'] else state['gather']} inside the timed region at N>1",
+                                   f"{env2._bench_mode} inside the timed region at N>1",
                        "layout": config2["layout"]},
             "roofline": fd_roofline(env2, B2, ms2 / K2, "f64", peaks),
             **({"gather_verified": config2["verified"]} if world > 1 else {}),
@@ -740,8 +762,10 @@ def main():
     ap.add_argument("--burnin", type=int, default=40, help="device burn-in periods before timing")
     ap.add_argument("--cpu-periods", type=int, default=20, help="control periods per host core for cpu_baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--gather", default="fused", choices=["fused", "nccl", "none"],
-                    help="N>1: how every rank gets the full batch each period (default: fused peer stores)")
+    ap.add_argument("--gather", default="fused", choices=["fused", "fused_mc", "fused_ipc", "nccl", "none"],
+                    help="N>1: how every rank gets the full batch each period.  fused (default): stores fused into the period "
+                         "kernel's epilogue -- fused_mc (symmetric memory + NVLS multicast stores) if it sets up and verifies on "
+                         "every rank, else fused_ipc (CUDA-IPC unicast peer stores), else nccl; the other values force one mode")
     ap.add_argument("--solver", default="fd_rk4", choices=["fd_rk4", "etdrk4"],
                     help="timed solver; the default is the reference's scheme (the headline), etdrk4 is the spectral mode")
     ap.add_argument("--no-spectral", action="store_true", help="skip the extra spectral-ETDRK4 leg")

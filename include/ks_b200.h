@@ -172,6 +172,17 @@ int ks_gather_connect(ks_handle *h, const void *all_handles);
 int ks_step_gather(ks_handle *h, const float *actions, void **gathered, void *stream);
 int ks_gather_status(ks_handle *h, int32_t *timed_out, void *stream);
 int ks_gather_clear(ks_handle *h, void *stream);
+/* Alternative set-up on buffers the CALLER has allocated and mapped -- any symmetric-memory mechanism
+ * (torch.distributed._symmetric_memory, NVSHMEM, cuMem* with fabric handles) instead of steps 1-3 above:
+ *   ks_gather_layout(h, world, &slot_bytes, &total_bytes)   size every rank's buffer must have
+ *   ks_gather_attach(h, world, rank, peer_bufs, multicast, bytes)
+ * peer_bufs[r] = rank r's buffer as mapped into THIS process (peer_bufs[rank] = the local one, which this call
+ * zero-fills; the caller synchronises the ranks before the first ks_step_gather).  `multicast` (nullable) = an NVLS
+ * multicast address bound to all of those buffers: the FD-RK4 period kernel then sends its observation rows ONCE
+ * with multimem.st (replicated by the NVSwitch) instead of once per peer; the small per-env outputs and the
+ * handshake stay unicast.  The library neither frees nor unmaps attached buffers. */
+int ks_gather_layout(const ks_handle *h, int32_t world, size_t *slot_bytes, size_t *total_bytes);
+int ks_gather_attach(ks_handle *h, int32_t world, int32_t rank, void *const *peer_bufs, void *multicast, size_t bytes);
 
 /* One step of the reference's data-collection plumbing, fused (two small kernels), for stores of
  * length 1 as the MBRL loop uses them (mbrl.py:257-275): what StoreNObsVecWrapper.step_wait

@@ -63,6 +63,8 @@ struct ks_handle {
     uint8_t *g_buf = nullptr;       // local: [2 parities][world][out_total] + flags [world] u32 (own cudaMalloc)
     uint8_t *g_peer[KS_MAX_WORLD] = {nullptr};   // every rank's buffer as mapped into this process (own = g_buf)
     bool g_connected = false;
+    bool g_external = false;        // buffers attached by the caller (ks_gather_attach): never freed / unmapped here
+    uint8_t *g_mc = nullptr;        // NVLS multicast alias of the gather buffers (nullable)
     uint32_t g_epoch = 0;
     int32_t *g_timeout = nullptr;   // device: [2] spare words + the table of every rank's flag array
     int32_t *g_timeout_host = nullptr;   // mapped pinned host word: 1 + rank of a peer that never signalled (sticky)
@@ -440,10 +442,11 @@ int gather_debug()
 
 int launch_period(ks_handle *h, int K, const float *actions, const float *phi, float *obs, double *reward,
                   uint8_t *truncated, int32_t *step, uint8_t *nonfinite_out, int reset_timestep, const uint8_t *mask,
-                  cudaStream_t stream, int n_remote = 0, const long long *remote_delta = nullptr)
+                  cudaStream_t stream, int n_remote = 0, const long long *remote_delta = nullptr, long long mc_delta = 0)
 {
     ks::Params p;
     p.n_remote = n_remote;
+    p.mc_delta = mc_delta;
     p.skip_fence = (n_remote > 0 && (gather_debug() & 1)) ? 1 : 0;
     for (int q = 0; q < ks::kMaxRemote; ++q) p.remote_delta[q] = q < n_remote ? remote_delta[q] : 0;
     p.u = h->u;
@@ -655,10 +658,10 @@ int ks_destroy(ks_handle *h)
         cudaFree(h->mask);
         cudaFree(h->collect_keys);
         cudaFree(h->etd_tables);
-        if (h->g_connected)
+        if (h->g_connected && !h->g_external)
             for (int r = 0; r < h->g_world; ++r)
                 if (r != h->g_rank && h->g_peer[r]) cudaIpcCloseMemHandle(h->g_peer[r]);
-        cudaFree(h->g_buf);
+        if (!h->g_external) cudaFree(h->g_buf);
         cudaFree(h->g_timeout);
         if (h->g_timeout_host) cudaFreeHost(h->g_timeout_host);
         cudaGetLastError();
@@ -970,9 +973,12 @@ int ks_step_gather(ks_handle *h, const float *actions, void **gathered, void *st
         uint8_t *theirs = h->g_peer[r] + parity_off + (size_t)h->g_rank * h->g_slot;
         delta[n++] = (long long)(theirs - mine);
     }
+    // multicast alias of this rank's slot (FD-RK4 kernel only; the spectral kernels use the unicast stores)
+    const long long mc_delta = (h->g_mc && h->cfg.solver == KS_SOLVER_FD_RK4 && h->g_world > 1)
+                                   ? (long long)((h->g_mc + parity_off + (size_t)h->g_rank * h->g_slot) - mine) : 0;
     int rc = launch_period(h, 1, actions, nullptr, (float *)(mine + h->out_off[1]), (double *)(mine + h->out_off[0]),
                            mine + h->out_off[3], (int32_t *)(mine + h->out_off[2]), mine + h->out_off[4], 0, nullptr, stream,
-                           n, delta);
+                           n, delta, mc_delta);
     if (rc != KS_OK) return rc;
     if (h->g_world > 1 && !(gather_debug() & 2)) {
         gather_signal_wait<<<1, 32, 0, stream>>>(reinterpret_cast<uint32_t *const *>(h->g_timeout + 2),
@@ -983,6 +989,59 @@ int ks_step_gather(ks_handle *h, const float *actions, void **gathered, void *st
         h->launches += 1;
     }
     if (gathered) *gathered = h->g_buf + parity_off;
+    return KS_OK;
+}
+
+int ks_gather_layout(const ks_handle *h, int32_t world, size_t *slot_bytes, size_t *total_bytes)
+{
+    if (!h || world < 1 || world > KS_MAX_WORLD) return KS_ERR_ARG;
+    const size_t slot = (h->out_total + 255) & ~size_t(255);
+    if (slot_bytes) *slot_bytes = slot;
+    if (total_bytes) *total_bytes = 2 * (size_t)world * slot + 256;
+    return KS_OK;
+}
+
+int ks_gather_attach(ks_handle *h, int32_t world, int32_t rank, void *const *peer_bufs, void *multicast, size_t bytes)
+{
+    if (!h || !peer_bufs) return h ? fail(h, KS_ERR_ARG, "ks_gather_attach: NULL argument") : KS_ERR_ARG;
+    if (world < 1 || world > KS_MAX_WORLD || rank < 0 || rank >= world)
+        return fail(h, KS_ERR_ARG, "ks_gather_attach: world=%d rank=%d (max world %d)", world, rank, KS_MAX_WORLD);
+    if (h->g_buf) return fail(h, KS_ERR_STATE, "ks_gather_attach: gather already initialised");
+    size_t slot = 0, total = 0;
+    ks_gather_layout(h, world, &slot, &total);
+    if (bytes < total) return fail(h, KS_ERR_ARG, "ks_gather_attach: buffers of %zu bytes, %zu needed", bytes, total);
+    for (int r = 0; r < world; ++r)
+        if (!peer_bufs[r]) return fail(h, KS_ERR_ARG, "ks_gather_attach: peer_bufs[%d] is NULL", r);
+    DeviceGuard guard(h->cfg.device);
+    h->g_world = world;
+    h->g_rank = rank;
+    h->g_slot = slot;
+    h->g_flags_off = 2 * (size_t)world * slot;
+    h->g_total = total;
+    h->g_external = true;
+    for (int r = 0; r < world; ++r) h->g_peer[r] = static_cast<uint8_t *>(peer_bufs[r]);
+    h->g_buf = h->g_peer[rank];
+    h->g_mc = static_cast<uint8_t *>(multicast);
+    KS_CUDA(h, cudaMemset(h->g_buf, 0, h->g_total));
+    KS_CUDA(h, cudaMalloc(&h->g_timeout, 2 * sizeof(int32_t) + KS_MAX_WORLD * sizeof(void *)));
+    KS_CUDA(h, cudaMemset(h->g_timeout, 0, 2 * sizeof(int32_t) + KS_MAX_WORLD * sizeof(void *)));
+    KS_CUDA(h, cudaHostAlloc((void **)&h->g_timeout_host, sizeof(int32_t), cudaHostAllocMapped));
+    *h->g_timeout_host = 0;
+    {
+        double seconds = 120.0;
+        if (const char *e = getenv("KS_GATHER_TIMEOUT_S")) {
+            const double v = atof(e);
+            if (v > 0.0) seconds = v;
+        }
+        int khz = 1965000;
+        cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, h->cfg.device);
+        h->g_timeout_cycles = (long long)(seconds * 1e3 * (double)khz);
+    }
+    uint32_t *flags[KS_MAX_WORLD] = {nullptr};
+    for (int r = 0; r < world; ++r) flags[r] = reinterpret_cast<uint32_t *>(h->g_peer[r] + h->g_flags_off);
+    KS_CUDA(h, cudaMemcpy(h->g_timeout + 2, flags, sizeof(flags), cudaMemcpyHostToDevice));
+    KS_CUDA(h, cudaDeviceSynchronize());
+    h->g_connected = true;
     return KS_OK;
 }
 

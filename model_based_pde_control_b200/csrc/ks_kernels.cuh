@@ -63,6 +63,10 @@ struct Params {
     // into this process with CUDA IPC, i.e. plain st.global over NVLink.  n_remote = 0 otherwise.
     int n_remote;
     int skip_fence;        // measurement knob (KS_GATHER_DEBUG=nofence): leave out the system-scope fence at kernel end
+    // NVLS multicast (ks_gather_attach with a multicast address): `pointer + mc_delta` is the multicast alias of this
+    // rank's slot in EVERY rank's gather buffer; the observation rows then leave the GPU once (multimem.st, replicated
+    // by the NVSwitch) instead of once per peer.  0 = not available.
+    long long mc_delta;
     long long remote_delta[kMaxRemote];
 };
 
@@ -70,6 +74,17 @@ template <typename U>
 __device__ __forceinline__ U *remote_ptr(U *local, long long delta)
 {
     return reinterpret_cast<U *>(reinterpret_cast<char *>(local) + delta);
+}
+
+// One store to an NVLS multicast address: the NVSwitch replicates it into every bound GPU's memory.
+__device__ __forceinline__ void multimem_st(float *mc, float4 v)
+{
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};"
+                 :: "l"(mc), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void multimem_st(float *mc, float v)
+{
+    asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" :: "l"(mc), "f"(v) : "memory");
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -447,16 +462,24 @@ __global__ void __launch_bounds__(kBlockThreads) ks_period_kernel(const Params p
                 for (int i4 = lane; i4 * 4 < nfl; i4 += 32) {
                     if (!((actmask >> ((i4 * 4) / P)) & 1u)) continue;
                     const float4 v = *reinterpret_cast<const float4 *>(srow + i4 * 4);
-                    *reinterpret_cast<float4 *>(wbase + i4 * 4) = v;
-                    for (int q = 0; q < p.n_remote; ++q)
-                        *reinterpret_cast<float4 *>(remote_ptr(wbase + i4 * 4, p.remote_delta[q])) = v;
+                    *reinterpret_cast<float4 *>(wbase + i4 * 4) = v;      // (local copy: visible here without a trip to the switch)
+                    if (p.mc_delta != 0) {
+                        multimem_st(remote_ptr(wbase + i4 * 4, p.mc_delta), v);
+                    } else {
+                        for (int q = 0; q < p.n_remote; ++q)
+                            *reinterpret_cast<float4 *>(remote_ptr(wbase + i4 * 4, p.remote_delta[q])) = v;
+                    }
                 }
             } else {
                 for (int i = lane; i < nfl; i += 32) {
                     if (!((actmask >> (i / P)) & 1u)) continue;
                     const float v = srow[i];
                     wbase[i] = v;
-                    for (int q = 0; q < p.n_remote; ++q) *remote_ptr(wbase + i, p.remote_delta[q]) = v;
+                    if (p.mc_delta != 0) {
+                        multimem_st(remote_ptr(wbase + i, p.mc_delta), v);
+                    } else {
+                        for (int q = 0; q < p.n_remote; ++q) *remote_ptr(wbase + i, p.remote_delta[q]) = v;
+                    }
                 }
             }
             __syncwarp();

@@ -535,6 +535,23 @@ class KSVecEnv(VectorEnvBase):
             raise ValueError("need one 64-byte IPC handle per rank, in rank order")
         _lib.check(self._h, self._lib.ks_gather_connect(self._h, blob))
 
+    def gather_layout(self, world: int) -> tuple[int, int]:
+        """``(slot_bytes, total_bytes)`` every rank's gather buffer needs for a world of ``world`` ranks."""
+        slot, total = ctypes.c_size_t(), ctypes.c_size_t()
+        _lib.check(self._h, self._lib.ks_gather_layout(self._h, world, ctypes.byref(slot), ctypes.byref(total)))
+        return int(slot.value), int(total.value)
+
+    def gather_attach(self, world: int, rank: int, peer_ptrs: Sequence[int], multicast_ptr: int = 0, nbytes: int = 0) -> None:
+        """Run the fused exchange on buffers the caller allocated and mapped (``ks_gather_attach``): symmetric
+        memory instead of CUDA IPC.  ``peer_ptrs[r]`` = rank r's buffer as mapped into this process;
+        ``multicast_ptr`` (0 = none) = an NVLS multicast address bound to all of them, which lets the period
+        kernel send its observation rows once (``multimem.st``) instead of once per peer."""
+        self._check_open()
+        arr = (ctypes.c_void_p * world)(*[int(p) for p in peer_ptrs])
+        _lib.check(self._h, self._lib.ks_gather_attach(self._h, world, rank, arr, ctypes.c_void_p(int(multicast_ptr) or None),
+                                                       int(nbytes)))
+        self._gather = dict(world=world, rank=rank, slot=self.gather_layout(world)[0], views={})
+
     def step_gather(self, actions: torch.Tensor) -> dict:
         """One control period of the local shard whose kernel epilogue also stores the outputs into
         every peer's gather buffer over NVLink (``ks_step_gather``).  Returns full-batch views

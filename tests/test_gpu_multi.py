@@ -40,7 +40,13 @@ ppl = int(os.environ.get("KS_PPL", "0"))                           # spectral so
 env = KSVecEnv(hi - lo, cfg, device=local, solver=solver, points_per_lane=ppl)          # fused path
 ref = KSVecEnv(hi - lo, cfg, device=local, solver=solver, points_per_lane=ppl)          # NCCL path
 env.set_state(u0[lo:hi], 0); ref.set_state(u0[lo:hi], 0)
-connect_fused_gather(env)
+if os.environ.get("KS_SYMM"):      # symmetric memory + NVLS multicast stores instead of CUDA IPC + unicast
+    from model_based_pde_control_b200.sharding import connect_fused_gather_symm
+    info = connect_fused_gather_symm(env)
+    if rank == 0:
+        print("SYMM", info, flush=True)
+else:
+    connect_fused_gather(env)
 fields = ref.packed_fields()
 ok = True
 for k in range(K):
@@ -112,7 +118,7 @@ dist.barrier(); dist.destroy_process_group()
 '''
 
 
-def _run(world, solver, timeout_case=False, ppl=0):
+def _run(world, solver, timeout_case=False, ppl=0, symm=False):
     import torch
 
     if torch.cuda.device_count() < world:
@@ -120,6 +126,8 @@ def _run(world, solver, timeout_case=False, ppl=0):
     env = dict(os.environ, KS_ROOT=ROOT, KS_SOLVER=solver, KS_PPL=str(ppl))
     if timeout_case:
         env.update(KS_TEST_TIMEOUT="1", KS_GATHER_TIMEOUT_S="0.5")
+    if symm:
+        env.update(KS_SYMM="1")
     path = os.path.join(ROOT, "gpurun_out", f"_multi_worker_{solver}.py")     # torchrun needs a script file
     os.makedirs(os.path.dirname(path), exist_ok=True)
     with open(path, "w") as f:
@@ -143,6 +151,13 @@ def test_fused_gather_4gpus():
 
 def test_fused_gather_8gpus():
     _run(8, "fd_rk4")
+
+
+@pytest.mark.parametrize("solver", ["fd_rk4", "etdrk4"])
+def test_fused_gather_on_symmetric_memory_with_multicast_2gpus(solver):
+    """ks_gather_attach: the same exchange on torch symmetric-memory buffers; the FD-RK4 kernel sends its
+    observation rows through the NVLS multicast address (multimem.st), the spectral kernels stay unicast."""
+    _run(2, solver, symm=True)
 
 
 def test_fused_gather_late_peer_is_reported_not_ignored():
