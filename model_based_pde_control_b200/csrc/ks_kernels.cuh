@@ -22,7 +22,10 @@
 
 namespace ks {
 
-constexpr int kBlockThreads = 128;
+#ifndef KS_BLOCK_THREADS
+#define KS_BLOCK_THREADS 128
+#endif
+constexpr int kBlockThreads = KS_BLOCK_THREADS;
 constexpr int kHalo = 4;
 constexpr unsigned kFullMask = 0xffffffffu;
 constexpr int kMaxRemote = 15;   // peers a launch can mirror its outputs to (world size <= 16)
