@@ -118,28 +118,40 @@ def connect_fused_gather_symm(env, group=None, multicast: bool = True) -> dict:
 
     group = group if group is not None else dist.group.WORLD
     world, rank = dist.get_world_size(group), dist.get_rank(group)
-    err, info = None, {}
+
+    def agree(stage, err, payload=None):
+        """Every rank learns every rank's outcome of `stage`; any failure raises on ALL ranks (nobody is left
+        alone inside the next collective)."""
+        outcomes = [None] * world
+        dist.all_gather_object(outcomes, (err, payload), group=group)
+        errors = [e for e, _ in outcomes if e]
+        if errors:
+            raise RuntimeError(f"fused gather (symmetric memory), {stage}: " + "; ".join(errors))
+        return [p for _, p in outcomes]
+
+    # 1. local allocation (no collective inside)
+    err, buf, total = None, None, 0
     try:
         _slot, total = env.gather_layout(world)
         buf = symm_mem.empty(total, dtype=torch.uint8, device=env.device)
+    except Exception as exc:      # noqa: BLE001 - agreed on below
+        err = f"rank {rank}: {type(exc).__name__}: {exc}"
+    sizes = agree("allocation", err, (env.num_envs, total))
+    if len(set(sizes)) != 1:
+        raise ValueError(f"fused gather needs equal shards, got {[n for n, _ in sizes]}")
+    # 2. rendezvous (collective: every rank is known to arrive) + attach
+    err, mc = None, 0
+    try:
         hdl = symm_mem.rendezvous(buf, group)
         mc = int(hdl.multicast_ptr) if multicast else 0
         env.gather_attach(world, rank, [int(p) for p in hdl.buffer_ptrs], mc, total)
         env._symm = (buf, hdl)            # keep the mapping alive as long as the env
-        info = {"multicast": bool(mc), "bytes": total}
-    except Exception as exc:      # noqa: BLE001 - agreed on below
+    except Exception as exc:      # noqa: BLE001
         err = f"rank {rank}: {type(exc).__name__}: {exc}"
-    outcomes = [None] * world
-    dist.all_gather_object(outcomes, (env.num_envs, err, info.get("multicast")), group=group)
-    errors = [e for _, e, _ in outcomes if e]
-    if errors:
-        raise RuntimeError("fused gather (symmetric memory): " + "; ".join(errors))
-    if len({n for n, _, _ in outcomes}) != 1:
-        raise ValueError(f"fused gather needs equal shards, got {[n for n, _, _ in outcomes]}")
-    info["multicast"] = all(bool(m) for _, _, m in outcomes) if multicast else False
+    flags = agree("rendezvous / attach", err, bool(mc))
     torch.cuda.synchronize(env.device)
     dist.barrier(group)      # every buffer zero-filled and attached before anybody's kernel writes into a peer
-    return info
+    return {"multicast": bool(multicast) and all(flags), "bytes": total}
 
 
 class ShardedKSVecEnv:

@@ -187,3 +187,48 @@ def test_fused_gather_setup_failure_is_raised_on_every_rank():
         p.join(120)
         assert p.exitcode == 0
     assert dict(q.get(timeout=5) for _ in range(3)) == {0: True, 1: True, 2: True}
+
+
+class SymmLayoutFailsEnv(StubGatherEnv):
+    """For ``connect_fused_gather_symm``: the local allocation stage fails on one rank only."""
+
+    device = torch.device("cpu")
+
+    def __init__(self, n, fail_rank):
+        super().__init__(n)
+        self.fail_rank = fail_rank
+
+    def gather_layout(self, world):
+        if dist.get_rank() == self.fail_rank:
+            raise OSError("no memory for the gather buffer")
+        return 256, 2 * world * 256 + 256
+
+
+def _symm_failing_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from model_based_pde_control_b200.sharding import connect_fused_gather_symm
+        try:
+            connect_fused_gather_symm(SymmLayoutFailsEnv(8, fail_rank=2))
+            q.put((rank, False))
+        except RuntimeError as exc:       # raised on EVERY rank before anybody enters the rendezvous collective
+            q.put((rank, "allocation" in str(exc) and "rank 2" in str(exc)))
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_symmetric_memory_setup_failure_is_agreed_on_before_the_rendezvous():
+    """One rank failing in the local allocation stage must not leave the others alone inside
+    ``symm_mem.rendezvous`` (a collective): the outcome of every stage is exchanged first."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_symm_failing_worker, args=(r, 3, port, q)) for r in range(3)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert dict(q.get(timeout=5) for _ in range(3)) == {0: True, 1: True, 2: True}
