@@ -659,15 +659,31 @@ class KSVecEnv(VectorEnvBase):
     def reward_func(self, obs, phi=None, *args, **kwargs):
         """``env.reward_func(obs, phi)`` (FuncTransform over ``l2control`` / ``dissipation``,
         kuramoto.py:64-73) for one observation ``(1,N)`` / ``(N,)`` -> scalar, or a batch
-        ``[M,(1,)N]`` -> ``[M]``; evaluated by the CUDA ``ks_eval`` kernel."""
+        ``[M,(1,)N]`` -> ``[M]``; evaluated by the CUDA ``ks_eval`` kernel in float64.  Like the reference's
+        ``FuncTransform`` the result comes back in the caller's container: NumPy in -> NumPy out, tensor in ->
+        tensor on the SAME device (``surrogates/training.py:214`` stacks CPU tensors and calls ``.numpy()``),
+        floating inputs keep their dtype."""
         is_np = not isinstance(obs, torch.Tensor)
-        o = np.asarray(obs, dtype=np.float64) if is_np else obs.to(torch.float64)
+        o = np.asarray(obs) if is_np else obs
+        in_dtype = o.dtype
         single = o.size == self.N if is_np else o.numel() == self.N
         if self.reward_mode == "dissipation" and phi is None:
             raise TypeError("dissipation reward needs phi")
-        r = self.evaluate(o.reshape(-1, self.N), None if phi is None else
-                          (np.asarray(phi, dtype=np.float32).reshape(-1, self.N) if not isinstance(phi, torch.Tensor)
-                           else phi.reshape(-1, self.N)), want=("reward",))["reward"]
+        if self.reward_mode == "l2":
+            phi = None          # the L2 objective ignores its second argument (callers pass phi or even the action there)
+        if is_np:
+            u = np.asarray(o, dtype=np.float64).reshape(-1, self.N)
+            p = None if phi is None else np.asarray(phi.detach().cpu() if isinstance(phi, torch.Tensor) else phi,
+                                                    dtype=np.float32).reshape(-1, self.N)
+            r = self.evaluate(u, p, want=("reward",))["reward"]
+            if np.issubdtype(in_dtype, np.floating):
+                r = r.astype(in_dtype, copy=False)
+            return r[0] if single else r
+        u = o.to(device=self.device, dtype=torch.float64).reshape(-1, self.N)
+        p = None if phi is None else torch.as_tensor(phi).to(device=self.device, dtype=torch.float32).reshape(-1, self.N)
+        r = self.evaluate(u, p, want=("reward",))["reward"].to(device=o.device)
+        if in_dtype.is_floating_point:
+            r = r.to(in_dtype)
         return r[0] if single else r
 
     # ------------------------------------------------------------------ teardown

@@ -148,9 +148,7 @@ class KSEnv(EnvBase):
         ``[M,(1,)N]`` -> ``[M]`` in ONE launch: ``mbrl/world/world.py:170`` calls it once per sample from
         a Python loop; replacing that list comprehension by ``self.reward_func(orescaled, arescaled)``
         costs one ``ks_eval`` launch per model step instead of one per sample."""
-        if self.vec.reward_mode == "l2":
-            phi = None          # the L2 objective ignores its second argument (the world model passes the ACTION there)
-        return self.vec.reward_func(obs, phi)
+        return self.vec.reward_func(obs, phi)      # (the L2 objective ignores phi: the world model passes the ACTION there)
 
     def render(self, mode="rgb_array"):
         raise NotImplementedError("rendering is not part of the control path (the reference has none either)")

@@ -232,6 +232,20 @@ def test_reward_func_and_forcing_helpers():
     assert np.allclose(got, want, rtol=1e-12)
     with pytest.raises(TypeError):
         d.reward_func(u)
+    # tensor in -> tensor out on the SAME device, floating dtype kept (surrogates/training.py:214 stacks CPU float32
+    # tensors and calls .numpy(); mbrl/world/world.py:170 passes float32 arrays and the ACTION as second argument)
+    import torch
+    t32 = torch.from_numpy(u[:, 0].astype(np.float32))
+    rs = torch.stack([env.reward_func(s, p) for s, p in zip(t32, torch.zeros(5, 64))], dim=0)
+    assert rs.device.type == "cpu" and rs.dtype == torch.float32 and rs.shape == (5,)
+    assert np.allclose(rs.numpy(), -(u[:, 0].astype(np.float32).astype(np.float64) ** 2).mean(axis=1), rtol=1e-6)
+    r32 = np.asarray([env.reward_func(o, a_) for o, a_ in zip(u.astype(np.float32), np.zeros((5, 1, 4), np.float32))], dtype=np.float32)
+    assert r32.shape == (5,) and np.allclose(r32, rs.numpy(), rtol=1e-6)
+    rc = env.reward_func(t32.cuda())
+    assert rc.is_cuda and rc.shape == (5,)
+    # env.rhs on NumPy rows as training.py:228 calls it: (rhs, (ux, uxx, uxxxx)), each shaped like the input
+    rhs, (ux, uxx, uxxxx) = env.rhs(u[0].astype(np.float32), phi)
+    assert rhs.shape == ux.shape == uxx.shape == uxxxx.shape == (1, 64)
     env.close(); d.close()
 
 

@@ -171,3 +171,29 @@ def test_result_blocks_are_reused_only_when_no_result_references_them():
     assert not spill["owned"] and all(spill is not b for b in fake._blocks)   # -> copy-out path
     del held
     assert free()["owned"]
+
+
+def test_forcing_object_inside_the_references_own_batch_transform():
+    """``mbrl.py:157`` / ``evaluation/evaluate.py:88`` wrap ``env.forcing`` in the reference's ``BatchTransform`` (and use
+    ``Operation([forcing, pdescaling])`` and ``.Inverse`` on it).  Our ``GaussianForcing`` inside the reference's own
+    container classes gives, bit for bit, what the reference's ``GaussianForcing`` gives there."""
+    from oracle import ref_loader
+
+    if not ref_loader.reference_available():
+        pytest.skip("reference tree not available")
+    _, tr = ref_loader.load_reference()
+    ref_env = ref_loader.make_reference_env()
+    ours = GaussianForcing(ref_env.x, ref_env.Xi, ref_env.sigma, ref_env.L, ref_env.N)
+    rng = np.random.default_rng(3)
+    acts = rng.uniform(-1, 1, (7, 1, 4)).astype(np.float32)                  # [B, C, A] as the replay stores them
+    a, b = tr.BatchTransform(ours), tr.BatchTransform(ref_env.forcing)
+    assert np.array_equal(a(acts), b(acts)) and a(acts).shape == (7, 1, 64)
+    t = torch.from_numpy(acts)
+    assert torch.equal(a(t), b(t))
+    phi = b(acts)
+    assert np.array_equal(a.Inverse(phi), b.Inverse(phi))                    # BatchTransform._Inverse -> forcing.Inverse per sample
+    assert np.allclose(a.Inverse(phi), acts, atol=2e-6)
+    scal = tr.Normalize(aggregate=True, batched=True)
+    scal.update(phi)
+    op_a, op_b = tr.Operation([a, scal]), tr.Operation([b, scal])            # evaluate.py:91
+    assert np.array_equal(op_a(acts), op_b(acts))
