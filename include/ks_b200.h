@@ -74,7 +74,7 @@ typedef struct ks_config {
     int32_t precision;         /* enum ks_precision */
     int32_t reward_mode;       /* enum ks_reward_mode */
     int32_t device;            /* CUDA device ordinal */
-    int32_t points_per_lane;   /* 0 = choose automatically; else P with N % P == 0, 4<=P<=16 */
+    int32_t points_per_lane;   /* 0 = choose automatically; else P with N % P == 0, 2<=P<=16 */
     int32_t obs_stride;        /* SensorTransform stride s: obs = u[s/2::s] (transforms.py:236-239);
                                   0 or 1 = full state (what the MBRL loop uses, mbrl.py:171,174) */
     int32_t solver;            /* enum ks_solver; 0 = the reference's FD-RK4 scheme */

@@ -158,17 +158,18 @@ void etd_tables_host(int N, double L, double h, bool dealias, std::vector<double
 }
 
 // Points per lane P for a grid of N points and a batch of B envs (lanes = N / P must fit one warp).
-// Static cost model fitted to B200 measurements (profiles/README.md sections 10 and 12), cycles per RK4
+// Static cost model fitted to B200 measurements (profiles/README.md sections 10, 12 and R2-7), cycles per RK4
 // sub-step of the fullest SM sub-partition (SMSP), which is what the launch takes:
 //     T(P) = max( L(P), w * c(P) ),   w = ceil(warps(P) / #SMSP),   warps(P) = ceil(B / (32 / lanes))
 //     c(P) = 182 P + 130   a warp's share of a saturated SMSP (859 / 1640 / 3048 cycles measured for
-//                          P = 4 / 8 / 16 at 65 536 envs)
+//                          P = 4 / 8 / 16 at 65 536 envs);  P < 4: 140 P + 280 (565-590 measured for P = 2)
 //     L(P) = 169 P + 430   one warp alone: its dependent-issue latency (1105 / 1915 / 3135 cycles
-//                          measured for P = 4 / 8 / 16)
-// Small batches therefore run with few points per lane (10 envs: 0.14 ms per period with P = 4
-// against 0.40 ms with P = 16), large ones with many (less halo overhead per point).  Smallest T
-// wins; a larger P wins ties within 0.5 %.  The choice is deterministic in (N, B, #SM) so that
-// every rank of a sharded run picks the same layout.
+//                          measured for P = 4 / 8 / 16);  P < 4: 140 P + 544 (824 measured for P = 2)
+// Small batches therefore run with few points per lane (up to 592 envs at N = 64: 0.105 ms per period with
+// P = 2, where the halo comes from two lanes on each side, against 0.138 ms with P = 4 and 0.40 ms with
+// P = 16), large ones with many (less halo overhead per point).  Smallest T wins; a larger P wins ties
+// within 0.5 %.  The choice is deterministic in (N, B, #SM) so that every rank of a sharded run picks
+// the same layout.
 int choose_points_per_lane(int N, long long B, int sm_count)
 {
     int best = 0;
@@ -181,8 +182,9 @@ int choose_points_per_lane(int N, long long B, int sm_count)
         const long long epw = 32 / lanes;
         const long long warps = (B + epw - 1) / epw;
         const long long per_smsp = (warps + smsp - 1) / smsp;
-        double t = (double)per_smsp * (182.0 * P + 130.0);
-        const double alone = 169.0 * P + 430.0;
+        const double share = P < 4 ? 140.0 * P + 280.0 : 182.0 * P + 130.0;
+        double t = (double)per_smsp * share;
+        const double alone = P < 4 ? 140.0 * P + 544.0 : 169.0 * P + 430.0;
         if (t < alone) t = alone;
         if (best == 0 || t <= best_t * 1.005) { best_t = t < best_t || best == 0 ? t : best_t; best = P; }
     }
@@ -529,10 +531,10 @@ int ks_create(const ks_config *cfg, ks_handle **out)
     int P = etd ? (cfg->N == 64 ? cfg->points_per_lane : 8) : cfg->points_per_lane;
     if (!etd && P != 0 && (P < ks::kMinP || P > ks::kMaxP || cfg->N % P || cfg->N / P > 32))
         return fail(nullptr, KS_ERR_UNSUPPORTED,
-                    "ks_create: N=%d needs N = lanes*P with 4<=P<=16, lanes<=32 (points_per_lane=%d)", cfg->N,
+                    "ks_create: N=%d needs N = lanes*P with 2<=P<=16, lanes<=32 (points_per_lane=%d)", cfg->N,
                     cfg->points_per_lane);
     if (!etd && P == 0 && choose_points_per_lane(cfg->N, cfg->num_envs, 0) == 0)
-        return fail(nullptr, KS_ERR_UNSUPPORTED, "ks_create: N=%d cannot be split as lanes*P with 4<=P<=16, lanes<=32",
+        return fail(nullptr, KS_ERR_UNSUPPORTED, "ks_create: N=%d cannot be split as lanes*P with 2<=P<=16, lanes<=32",
                     cfg->N);
 
     int ndev = 0;

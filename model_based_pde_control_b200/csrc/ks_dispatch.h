@@ -4,7 +4,7 @@
 
 namespace ks {
 
-constexpr int kMinP = 4;
+constexpr int kMinP = 2;
 constexpr int kMaxP = 16;
 
 // One translation unit per (precision, reward mode) so that the units compile in parallel.
@@ -27,6 +27,8 @@ const void *etd16_kernel_f32(int reward_mode);
     const void *ks::NAME(int P)                                                              \
     {                                                                                        \
         switch (P) {                                                                         \
+            case 2: return (const void *)&ks::ks_period_kernel<T, 2, RMODE>;                 \
+            case 3: return (const void *)&ks::ks_period_kernel<T, 3, RMODE>;                 \
             case 4: return (const void *)&ks::ks_period_kernel<T, 4, RMODE>;                 \
             case 5: return (const void *)&ks::ks_period_kernel<T, 5, RMODE>;                 \
             case 6: return (const void *)&ks::ks_period_kernel<T, 6, RMODE>;                 \

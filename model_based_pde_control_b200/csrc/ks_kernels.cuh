@@ -2,7 +2,7 @@
 //
 // One launch advances every environment of the handle by K control periods (K = 1 for
 // ks_step, K = burn-in length for ks_reset).  Layout: an environment's N grid points are
-// spread over `lanes` adjacent lanes of ONE warp, P = N / lanes contiguous points per lane, all
+// spread over `lanes` adjacent lanes of ONE warp, P = N / lanes contiguous points per lane (2..16), all
 // state in registers for the whole launch.  The +-4 point halo of the periodic finite-difference
 // stencils comes from the two neighbouring lanes by warp shuffle; HBM is touched only at
 // control-period boundaries (128-bit loads/stores of the state, float32 observation, reward).
@@ -201,17 +201,21 @@ struct RewardAcc {
 // ---------------------------------------------------------------------------------------------
 template <typename T, int P, int STAGE, int RMODE>
 __device__ __forceinline__ void rk4_stage(T (&u)[P], T (&us)[P], T (&acc)[P], const T (&phi)[P],
-                                          RewardAcc<T> &racc, const Coef<T> &c, int srcL, int srcR)
+                                          RewardAcc<T> &racc, const Coef<T> &c, int srcL, int srcR, int srcL2, int srcR2)
 {
     constexpr int H = kHalo;
+    static_assert(2 * P >= H, "the halo must come from at most two lanes on each side");
     T h[P + 2 * H];
 #pragma unroll
     for (int i = 0; i < P; ++i) h[H + i] = (STAGE == 0) ? u[i] : us[i];
-    // periodic halo: my left halo = last H points of the lane to the left, and vice versa
+    // periodic halo: my left halo = the H points before my first one -- the last H points of the lane to the left
+    // (P >= 4), or the points of the two lanes to the left (P = 2, 3: the small-batch layouts) -- and vice versa
 #pragma unroll
     for (int k = 0; k < H; ++k) {
-        h[k] = __shfl_sync(kFullMask, h[P + k], srcL);
-        h[P + H + k] = __shfl_sync(kFullMask, h[H + k], srcR);
+        const int hopL = (H - k + P - 1) / P, regL = P * hopL + k - H;      // my point k - H lives there
+        const int hopR = k / P + 1, regR = k % P;                            // my point P + k lives there
+        h[k] = __shfl_sync(kFullMask, h[H + regL], hopL == 1 ? srcL : srcL2);
+        h[P + H + k] = __shfl_sync(kFullMask, h[H + regR], hopR == 1 ? srcR : srcR2);
     }
 
     T q[P + 2 * H];
@@ -351,6 +355,8 @@ __global__ void __launch_bounds__(kBlockThreads) ks_period_kernel(const Params p
     const int base = sub * p.lanes;
     const int srcL = active ? base + (l + p.lanes - 1) % p.lanes : lane;
     const int srcR = active ? base + (l + 1) % p.lanes : lane;
+    const int srcL2 = active ? base + (l + 2 * p.lanes - 2) % p.lanes : lane;    // two lanes away (P < 4 only)
+    const int srcR2 = active ? base + (l + 2) % p.lanes : lane;
     const size_t off = (size_t)env * p.N + (size_t)(active ? l : 0) * P;
 
     T u[P], us[P], acc[P], phi[P];
@@ -391,10 +397,10 @@ __global__ void __launch_bounds__(kBlockThreads) ks_period_kernel(const Params p
         // ---- cfg_steps classic RK4 sub-steps, reward of the pre-step state ----
         RewardAcc<T> racc{T(0), T(0), T(0)};
         for (int s = 0; s < p.cfg_steps; ++s) {
-            rk4_stage<T, P, 0, RMODE>(u, us, acc, phi, racc, c, srcL, srcR);
-            rk4_stage<T, P, 1, RMODE>(u, us, acc, phi, racc, c, srcL, srcR);
-            rk4_stage<T, P, 2, RMODE>(u, us, acc, phi, racc, c, srcL, srcR);
-            rk4_stage<T, P, 3, RMODE>(u, us, acc, phi, racc, c, srcL, srcR);
+            rk4_stage<T, P, 0, RMODE>(u, us, acc, phi, racc, c, srcL, srcR, srcL2, srcR2);
+            rk4_stage<T, P, 1, RMODE>(u, us, acc, phi, racc, c, srcL, srcR, srcL2, srcR2);
+            rk4_stage<T, P, 2, RMODE>(u, us, acc, phi, racc, c, srcL, srcR, srcL2, srcR2);
+            rk4_stage<T, P, 3, RMODE>(u, us, acc, phi, racc, c, srcL, srcR, srcL2, srcR2);
         }
 
         // ---- period epilogue: reward, flags, observation ----

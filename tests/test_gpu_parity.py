@@ -71,7 +71,8 @@ def test_golden_trajectory_free_running():
     env.close()
 
 
-@pytest.mark.parametrize("N,L,J,P", [(64, 22.0, 4, 0), (64, 22.0, 4, 4), (64, 22.0, 4, 16), (256, 88.0, 8, 0),
+@pytest.mark.parametrize("N,L,J,P", [(64, 22.0, 4, 0), (64, 22.0, 4, 2), (64, 22.0, 4, 4), (64, 22.0, 4, 16), (256, 88.0, 8, 0),
+                                     (48, 16.5, 3, 3), (30, 10.3125, 2, 3), (18, 6.1875, 1, 2),
                                      (256, 88.0, 8, 16), (128, 44.0, 4, 0), (96, 33.0, 4, 0), (96, 33.0, 3, 8),
                                      (100, 34.375, 5, 0), (32, 11.0, 2, 0), (16, 5.5, 1, 0), (512, 176.0, 8, 0)])
 def test_random_batch_vs_oracle(N, L, J, P):
@@ -260,13 +261,13 @@ def test_state_is_independent_of_the_lane_layout():
     u0 = rng.uniform(-2, 2, (B, 64))
     a = rng.uniform(-1, 1, (B, 4)).astype(np.float32)
     out = {}
-    for P in (4, 8, 16):
+    for P in (2, 4, 8, 16):
         env = KSVecEnv(B, dict(cfg_steps=40), points_per_lane=P)
         env.set_state(u0, 0)
         _, r, *_ = env.step(a)
         out[P] = (env.get_state()[0], r)
         env.close()
-    for P in (8, 16):
+    for P in (2, 8, 16):
         assert np.array_equal(out[P][0], out[4][0])
         assert np.abs(out[P][1] / out[4][1] - 1).max() < 1e-14
 
