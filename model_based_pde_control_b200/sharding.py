@@ -159,8 +159,10 @@ class ShardedKSVecEnv:
 
     ``step_device(actions)`` takes the FULL action batch ``[num_envs, J]`` (every rank holds the
     replicated policy output), steps the local shard, and all-gathers the results so that every
-    rank returns full-batch tensors.  Results equal the single-GPU run bit for bit because an
-    env's arithmetic does not depend on where it lives.
+    rank returns full-batch tensors.  States and observations equal the single-GPU run bit for bit because
+    an env's arithmetic does not depend on where it lives; so do the rewards when ``points_per_lane=`` pins the
+    lane layout (their summation order follows the layout, which the library otherwise picks from the LOCAL
+    batch size -- a shard may get another layout than the whole batch: equal to 1e-15 then).
 
     ``env_factory(local_num_envs)`` builds the local env (default: ``KSVecEnv``).
     """

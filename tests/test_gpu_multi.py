@@ -60,7 +60,9 @@ assert not env.gather_timed_out()
 
 # the gathered batch equals the single-GPU run of all envs (rank 0 computes it)
 if rank == 0:
-    full = KSVecEnv(B_total, cfg, device=local, solver=solver, points_per_lane=ppl)
+    # same lane layout as the shards: the STATE is bitwise independent of the layout, the reward's summation order
+    # follows it (the chooser picks P from the batch size, and a 510-env shard gets another P than 1020 envs)
+    full = KSVecEnv(B_total, cfg, device=local, solver=solver, points_per_lane=env.launch_info()["points_per_lane"])
     full.set_state(u0, 0)
     for k in range(K):
         f = full.step_device(acts[k])
