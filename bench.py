@@ -166,7 +166,8 @@ def shared_config(B, world, N, L, J, S, dt, precision, gather):
         "workload": workload_name(B, world, N, L, J, S, dt, precision),
         "envs_per_gpu": B, "total_envs": B * world, "N": N, "J": J, "cfg_steps": S,
         "l2": "GPU arm: L2 flushed (256 MiB memset) between timed steps, outside the per-step CUDA-event pairs; at N>1 the "
-              "ranks are re-aligned after each flush by a 4-byte all-reduce, also outside the pairs.  CPU arm: not applicable",
+              "ranks are re-aligned after each flush by a 4-byte all-reduce + (fused exchange) the library's device-side flag "
+              "rendezvous, also outside the pairs.  CPU arm: not applicable",
         "collective": "GPU arm at N>1 (--gather %s): %s; N=1 and CPU arm: none" % (gather, {
             "fused": "the period kernel's epilogue stores the packed obs/reward/step/truncated/flags block into every rank's "
                      "gather buffer over NVLink + one-warp epoch handshake, inside the timed region; `gather_mode` says which "
@@ -512,9 +513,13 @@ def run_gpu_arm(args):
             flush.zero_()                      # L2 flush between timed steps (outside the event pair)
             if world > 1:
                 # the 256 MiB memsets do not take equally long on every GPU; re-align the ranks on the
-                # device (stream-ordered 4-byte all-reduce, outside the event pair) so that a timed step
-                # is the period + exchange, not the previous flush's skew
+                # device (stream-ordered, outside the event pair) so that a timed step is the period +
+                # exchange, not the previous flush's skew: a 4-byte all-reduce, followed -- when the fused
+                # exchange is connected -- by the library's own flag rendezvous (ks_gather_barrier), which
+                # every rank leaves within about one NVLink flag flight (NCCL kernels exit a few us apart)
                 dist.all_reduce(align)
+                if fused(env) and not args.no_flag_barrier:
+                    env.gather_barrier()
             starts[k].record(stream)
             step(actions[Wsteps + k])
             stops[k].record(stream)
@@ -774,6 +779,7 @@ def main():
     ap.add_argument("--no-episode", action="store_true", help="skip e2e_episode_amortised")
     ap.add_argument("--no-config-65536", action="store_true")
     ap.add_argument("--no-large-domain", action="store_true")
+    ap.add_argument("--no-flag-barrier", action="store_true", help="N>1: re-align the ranks between timed steps with the all-reduce only")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)

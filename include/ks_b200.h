@@ -172,6 +172,10 @@ int ks_gather_connect(ks_handle *h, const void *all_handles);
 int ks_step_gather(ks_handle *h, const float *actions, void **gathered, void *stream);
 int ks_gather_status(ks_handle *h, int32_t *timed_out, void *stream);
 int ks_gather_clear(ks_handle *h, void *stream);
+/* Stream-ordered rendezvous of all ranks on the device (the exchange's one-warp signal / wait kernel with its own
+ * flag words and epoch counter, no payload): work enqueued after it starts within about one NVLink flag flight on
+ * every rank.  bench.py uses it to re-align the ranks between timed steps; all ranks must call it equally often. */
+int ks_gather_barrier(ks_handle *h, void *stream);
 /* Alternative set-up on buffers the CALLER has allocated and mapped -- any symmetric-memory mechanism
  * (torch.distributed._symmetric_memory, NVSHMEM, cuMem* with fabric handles) instead of steps 1-3 above:
  *   ks_gather_layout(h, world, &slot_bytes, &total_bytes)   size every rank's buffer must have

@@ -88,6 +88,7 @@ EXPORTS = {
     "ks_step_gather": (ctypes.c_int, [_vp, _vp, ctypes.POINTER(_vp), _vp]),
     "ks_gather_status": (ctypes.c_int, [_vp, ctypes.POINTER(_i32), _vp]),
     "ks_gather_clear": (ctypes.c_int, [_vp, _vp]),
+    "ks_gather_barrier": (ctypes.c_int, [_vp, _vp]),
     "ks_gather_layout": (ctypes.c_int, [_vp, _i32, ctypes.POINTER(ctypes.c_size_t), ctypes.POINTER(ctypes.c_size_t)]),
     "ks_gather_attach": (ctypes.c_int, [_vp, _i32, _i32, ctypes.POINTER(_vp), _vp, ctypes.c_size_t]),
     "ks_collect": (ctypes.c_int, [_vp, ctypes.POINTER(KsCollectArgs), _vp]),

@@ -66,6 +66,7 @@ struct ks_handle {
     bool g_external = false;        // buffers attached by the caller (ks_gather_attach): never freed / unmapped here
     uint8_t *g_mc = nullptr;        // NVLS multicast alias of the gather buffers (nullable)
     uint32_t g_epoch = 0;
+    uint32_t g_barrier_epoch = 0;   // ks_gather_barrier's own epochs (second flag array of the flag block)
     int32_t *g_timeout = nullptr;   // device: [2] spare words + the table of every rank's flag array
     int32_t *g_timeout_host = nullptr;   // mapped pinned host word: 1 + rank of a peer that never signalled (sticky)
     long long g_timeout_cycles = 0;
@@ -328,16 +329,18 @@ __global__ void eval_rows(int M, int N, double dx, int reward_mode, const double
 // lives in mapped host memory so that the next ks_step_gather / ks_gather_status sees it without a
 // synchronise and fails, and it poisons the missing peer's slot (non-finite flags = 0xFF) so that a
 // consumer that validates flags rejects the stale data even before the host has looked.
+// `word0` selects the flag array inside the 256-byte flag block: 0 = the exchange's epochs, KS_MAX_WORLD = the
+// stand-alone rendezvous of ks_gather_barrier (its own epoch counter; poison_len = 0 there).
 __global__ void gather_signal_wait(uint32_t *const *peer_flags, volatile uint32_t *local_flags, int world, int rank,
                                    uint32_t epoch, volatile int32_t *timeout, long long max_cycles, uint8_t *poison_base,
-                                   size_t slot_bytes, size_t poison_off, int poison_len)
+                                   size_t slot_bytes, size_t poison_off, int poison_len, int word0)
 {
     const int r = threadIdx.x;
     if (r >= world || r == rank) return;
     __threadfence_system();
-    *reinterpret_cast<volatile uint32_t *>(peer_flags[r] + rank) = epoch;
+    *reinterpret_cast<volatile uint32_t *>(peer_flags[r] + word0 + rank) = epoch;
     const long long t0 = clock64();
-    while ((int32_t)(local_flags[r] - epoch) < 0) {
+    while ((int32_t)(local_flags[word0 + r] - epoch) < 0) {
         if (clock64() - t0 > max_cycles) {
             *timeout = 1 + r;
             uint8_t *bad = poison_base + (size_t)r * slot_bytes + poison_off;
@@ -986,11 +989,32 @@ int ks_step_gather(ks_handle *h, const float *actions, void **gathered, void *st
         gather_signal_wait<<<1, 32, 0, stream>>>(reinterpret_cast<uint32_t *const *>(h->g_timeout + 2),
                                                  reinterpret_cast<volatile uint32_t *>(h->g_buf + h->g_flags_off), h->g_world,
                                                  h->g_rank, h->g_epoch, h->g_timeout_host, h->g_timeout_cycles,
-                                                 h->g_buf + parity_off, h->g_slot, h->out_off[4], h->cfg.num_envs);
+                                                 h->g_buf + parity_off, h->g_slot, h->out_off[4], h->cfg.num_envs, 0);
         KS_CUDA(h, cudaGetLastError());
         h->launches += 1;
     }
     if (gathered) *gathered = h->g_buf + parity_off;
+    return KS_OK;
+}
+
+int ks_gather_barrier(ks_handle *h, void *stream_)
+{
+    if (!h) return KS_ERR_ARG;
+    if (!h->g_buf || (h->g_world > 1 && !h->g_connected))
+        return fail(h, KS_ERR_STATE, "ks_gather_barrier: gather not initialised / connected");
+    if (h->g_world < 2) return KS_OK;
+    if (h->g_timeout_host && *(volatile int32_t *)h->g_timeout_host != 0)
+        return fail(h, KS_ERR_STATE, "ks_gather_barrier: rank %d never signalled earlier (ks_gather_clear re-arms)",
+                    *(volatile int32_t *)h->g_timeout_host - 1);
+    DeviceGuard guard(h->cfg.device);
+    h->g_barrier_epoch += 1;
+    gather_signal_wait<<<1, 32, 0, (cudaStream_t)stream_>>>(reinterpret_cast<uint32_t *const *>(h->g_timeout + 2),
+                                                            reinterpret_cast<volatile uint32_t *>(h->g_buf + h->g_flags_off),
+                                                            h->g_world, h->g_rank, h->g_barrier_epoch, h->g_timeout_host,
+                                                            h->g_timeout_cycles, h->g_buf, h->g_slot, h->out_off[4], 0,
+                                                            KS_MAX_WORLD);
+    KS_CUDA(h, cudaGetLastError());
+    h->launches += 1;
     return KS_OK;
 }
 

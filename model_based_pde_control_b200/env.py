@@ -594,6 +594,10 @@ class KSVecEnv(VectorEnvBase):
         """Re-arm the fused exchange after a time-out (the application has re-synchronised its ranks)."""
         _lib.check(self._h, self._lib.ks_gather_clear(self._h, self._stream()))
 
+    def gather_barrier(self) -> None:
+        """Stream-ordered device-side rendezvous of all ranks (``ks_gather_barrier``; no host synchronisation)."""
+        _lib.check(self._h, self._lib.ks_gather_barrier(self._h, self._stream()))
+
     def rollout_device(self, actions: Optional[torch.Tensor], K: Optional[int] = None, outputs: bool = True) -> dict:
         """``K`` control periods in ONE persistent launch (open loop).  ``actions``: CUDA float32
         ``[K,B,J]`` or ``None`` for no-op periods (then ``K`` is required)."""

@@ -50,6 +50,8 @@ else:
 fields = ref.packed_fields()
 ok = True
 for k in range(K):
+    if k % 3 == 1:
+        env.gather_barrier()           # device-side rendezvous with its own flag words: must not disturb the exchange's epochs
     g = env.step_gather(acts[k, lo:hi])
     o = ref.step_device(acts[k, lo:hi])
     n = gather_packed(o["packed"], fields, hi - lo)
