@@ -123,6 +123,28 @@ def test_phi_override_equals_in_kernel_forcing():
     env.close()
 
 
+def test_dissipation_reward_mode_vs_reference_closure():
+    """The intended reward against vectors produced by the REFERENCE'S OWN ``dissipation`` closure and ``rhs``
+    (``tests/golden/make_golden_dissipation.py``; ``env.step`` itself raises in that mode): the batched
+    ``ks_eval`` reward and one whole control period on the default and on the large domain."""
+    from model_based_pde_control_b200 import KSVecEnv
+
+    g = load_golden("dissipation_kat")
+    env = KSVecEnv(1, reward_mode="dissipation")
+    r = env.reward_func(g["U"], g["PHI"])
+    assert np.abs(r / g["reward"] - 1).max() <= 1e-12
+    env.set_state(g["u0"][None], 0)
+    obs, rew, *_ = env.step(g["a1"])
+    assert rel_l2(env.get_state()[0][0], g["u1"]) <= TOL64 and abs(rew[0] / float(g["r1"]) - 1) <= TOL64
+    env.close()
+    big = KSVecEnv(1, dict(L=88.0, N=256, cfg_steps=int(g["cfg_steps_large"])), Xi=[k / 8 for k in range(8)],
+                   reward_mode="dissipation")
+    big.set_state(g["u0_large"][None], 0)
+    obs, rew, *_ = big.step(g["a8"])
+    assert rel_l2(big.get_state()[0][0], g["u1_large"]) <= TOL64 and abs(rew[0] / float(g["r1_large"]) - 1) <= TOL64
+    big.close()
+
+
 def test_dissipation_reward_mode_vs_oracle():
     from model_based_pde_control_b200 import KSVecEnv
     from oracle import ks_c, ks_numpy as ko
