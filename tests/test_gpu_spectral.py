@@ -293,3 +293,23 @@ def test_burnin_reaches_the_attractor():
     m = (u * u).mean()
     assert 1.0 < m < 2.5, m          # FD reference fixture: 1.43 under random actions; unforced is bimodal
     env.close()
+
+
+def test_reset_pool_uses_the_parents_solver():
+    """reset_mode="pool" with the spectral solver: the burner must be the parent's twin (same solver, dt, dealiasing) --
+    an FD-RK4 burner at dt = 0.025 would blow up and inject non-finite states."""
+    B = 12
+    env = make_env(B, Tmax=0.75, burnin_periods=6, reset_mode="pool", pool_slots=2, ic="device")
+    assert env.max_episode_steps == 3
+    env.reset(seed=1)
+    a = np.zeros((B, 4), np.float32)
+    for ep in range(3):
+        for k in range(3):
+            obs, rew, term, trunc, info = env.step(a)          # would raise FloatingPointError on a blown-up pool state
+        assert trunc.all() and np.isfinite(obs).all() and (info["step"] == 3).all()
+    pool = env._pool
+    assert pool is not None and pool.burner.solver == "etdrk4" and pool.burner.dt == env.dt
+    assert pool.burner.launch_info()["lanes_per_env"] == env.launch_info()["lanes_per_env"]
+    u, ts = env.get_state()
+    assert (ts == 0).all() and np.abs(u).max() < 10.0
+    env.close()
